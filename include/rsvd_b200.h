@@ -1,0 +1,126 @@
+/* rsvd_b200.h — the thin C-ABI device layer of the B200-native RSVDPACK hot path.
+ *
+ * Everything below is `extern "C"`, plain pointers and 64-bit sizes, no C++/torch types.  Matrices are
+ * dense column-major FP64 (d[col*ld + row], the reference's layout — matrix_vector_functions_intel_mkl.c:47-55),
+ * and every `double *` parameter is a DEVICE pointer unless its name starts with `h_`.
+ *
+ * Who calls this: the C host code that exports the reference's own API
+ * (include/rank_revealing_algorithms_intel_mkl.h, include/matrix_vector_functions_intel_mkl.h and their
+ * 64bit/ twins).  Each entry point names the reference wrapper (file:line under
+ * /root/reference/multi_core_mkl_code/, RRA = rank_revealing_algorithms_intel_mkl.c,
+ * MVF = matrix_vector_functions_intel_mkl.c) whose vendor call it replaces.
+ *
+ * All functions return 0 on success, non-zero on error; the message is kept for rsvd_b200_last_error().
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with an error.
+ */
+#ifndef RSVD_B200_H
+#define RSVD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef long long rsvd_i64;
+
+/* ---- context, errors, options -------------------------------------------------------------------- */
+int rsvd_b200_init(int device);                 /* implicit on first use (device 0 or $RSVD_B200_DEVICE / LOCAL_RANK) */
+int rsvd_b200_device_count(void);
+int rsvd_b200_status(void);                     /* 0 = no error since last clear */
+const char *rsvd_b200_last_error(void);
+void rsvd_b200_clear_error(void);
+void *rsvd_b200_stream(void);                   /* the cudaStream_t all kernels are launched on */
+void rsvd_b200_sync(void);
+unsigned long long rsvd_b200_launch_count(void); /* kernels launched by this library so far */
+/* options: "seed" (Omega seed, default 777 = the reference's unused `#define SEED 777`, MVH:10),
+ * "verbose", "force_generic_gemm", "force_qr_fallback" */
+void rsvd_b200_set_option(const char *name, rsvd_i64 value);
+rsvd_i64 rsvd_b200_get_option(const char *name); /* also "last_gemm_path", "last_qr_path", "qr_fallbacks", "sms" */
+
+/* ---- memory --------------------------------------------------------------------------------------- */
+double *rsvd_b200_dev_alloc(rsvd_i64 n_doubles);
+void rsvd_b200_dev_free(double *d);
+int rsvd_b200_h2d(double *d_dst, const double *h_src, rsvd_i64 n_doubles);  /* staged through pinned buffers if h_src is pageable */
+int rsvd_b200_d2h(double *h_dst, const double *d_src, rsvd_i64 n_doubles);
+void *rsvd_b200_host_alloc(size_t bytes);       /* pinned, zero-initialised (matrix_new for large mats, MVF:8-16) */
+void rsvd_b200_host_free(void *p);
+
+/* ---- primitives ----------------------------------------------------------------------------------- */
+/* cblas_dgemm NN/TN/NT (MVF:538-561): C = alpha*op(A)*op(B) + beta*C. */
+int rsvd_b200_gemm(char ta, char tb, rsvd_i64 m, rsvd_i64 n, rsvd_i64 k, double alpha, const double *A, rsvd_i64 lda,
+                   const double *B, rsvd_i64 ldb, double beta, double *C, rsvd_i64 ldc);
+/* initialize_random_matrix + dgemm fused (MVF:458-486 + MVF:538-552; RRA:90-95, RRA:1871-1877):
+ * C(m x n) = op(A)(m x k) * Omega(k x n) with Omega(kk, j) = normal(seed, off + kk*sk + j*sc) generated on the fly. */
+int rsvd_b200_sketch(char ta, rsvd_i64 m, rsvd_i64 n, rsvd_i64 k, const double *A, rsvd_i64 lda, uint64_t seed,
+                     rsvd_i64 sk, rsvd_i64 sc, rsvd_i64 off, double *C, rsvd_i64 ldc);
+/* initialize_random_matrix alone (MVF:458-486): d[i] = normal(seed, first + i). */
+int rsvd_b200_fill_normal(double *d, rsvd_i64 n, uint64_t seed, rsvd_i64 first);
+/* QR_factorization_getQ / compact_QR_factorization (MVF:1251-1263, 1214-1245; dgeqrf+dorgqr):
+ * Y (m x l) <- Q in place; R (l x l upper, may be NULL).  CholeskyQR2, TSQR-preconditioned fallback. */
+int rsvd_b200_orthonormalize(double *Y, rsvd_i64 ldy, rsvd_i64 m, rsvd_i64 l, double *R, rsvd_i64 ldr);
+/* pivotedQR_mkl (RRA:924-976; dgeqp3): in place, R in the upper triangle, jpvt 0-based stored as doubles. */
+int rsvd_b200_geqp3(double *A, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n, double *jpvt);
+/* singular_value_decomposition (MVF:1270-1284; dgesvd 'S','S') for square n x n: A = U diag(s) Vt, s descending. */
+int rsvd_b200_svd_small(double *A, rsvd_i64 lda, rsvd_i64 n, double *U, rsvd_i64 ldu, double *s, double *Vt, rsvd_i64 ldvt);
+/* compute_evals_and_evecs_of_symm_matrix (MVF:1206-1209; dsyev 'V','U'): ascending w, vectors overwrite A. */
+int rsvd_b200_eig_small(double *A, rsvd_i64 lda, rsvd_i64 n, double *w);
+/* upper_triangular_system_solve type 1 (MVF:1477-1493; dtrsm L,U,N,N): B <- R^{-1} B. */
+int rsvd_b200_trsm_left_upper(const double *R, rsvd_i64 ldr, rsvd_i64 k, double *B, rsvd_i64 ldb, rsvd_i64 ncols);
+/* square_matrix_system_solve (MVF:1525-1531; dgesv): B <- A^{-1} B, A overwritten by LU. */
+int rsvd_b200_lu_solve(double *A, rsvd_i64 lda, rsvd_i64 n, double *B, rsvd_i64 ldb, rsvd_i64 nrhs);
+/* get_matrix_frobenius_norm (MVF:360-372). */
+double rsvd_b200_frob_norm(const double *A, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n);
+/* matrix_build_transpose (MVF:246-253): B(n x m) = A(m x n)^T. */
+int rsvd_b200_transpose(const double *A, rsvd_i64 lda, double *B, rsvd_i64 ldb, rsvd_i64 m, rsvd_i64 n);
+
+/* ---- device-resident algorithms (inputs and outputs stay in HBM) -------------------------------------- */
+/* low_rank_svd_rand_decomp_fixed_rank (RRA:73-234).  A m x n (not modified).  omega: NULL = fused Philox
+ * (seed), else an imported n x (k+p) Omega.  Outputs U m x k, S k (singular values; vnum 1 descending, vnum 2
+ * ascending like the reference), V n x k. */
+int rsvd_b200_svd_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int vnum,
+                           int q, int s, uint64_t seed, const double *omega, double *U, rsvd_i64 ldu, double *S,
+                           double *V, rsvd_i64 ldv);
+/* randQB_pb_new (RRA:1576-1801).  Awork m x n is OVERWRITTEN by the residual A - QB (the reference's private
+ * copy, RRA:1630).  Q m x (kstep*nstep_max), B (kstep*nstep_max) x n; *frank = columns actually produced.
+ * nstep <= 0: tolerance mode (absolute Frobenius norm < tol, RRA:1773-1775), evaluated on the device. */
+int rsvd_b200_randqb_dev(double *Awork, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 kstep, rsvd_i64 nstep, double tol,
+                         int q, int s, uint64_t seed, double *Q, rsvd_i64 ldq, double *B, rsvd_i64 ldb, rsvd_i64 *frank);
+/* tail shared by RRA:133-225 and RRA:289-380: SVD factors from A and an orthonormal Q (m x l). */
+int rsvd_b200_svd_from_q_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, double *Q, rsvd_i64 ldq, rsvd_i64 l,
+                             rsvd_i64 k, int vnum, double *U, rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv);
+/* id_rand_decomp_fixed_rank (RRA:1863-1965): I (n doubles, 0-based permutation), T k x (n-k). */
+int rsvd_b200_id_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q, int s,
+                          uint64_t seed, const double *omega, double *I, double *T, rsvd_i64 ldt);
+/* id_decomp_fixed_rank_or_prec, k == min(m,n) branch (RRA:1830-1850): full pivoted QR of M (k x n). */
+int rsvd_b200_id_full_dev(const double *M, rsvd_i64 k, rsvd_i64 n, rsvd_i64 ldm, double *I, double *T, rsvd_i64 ldt);
+/* id_two_sided_rand_decomp_fixed_rank (RRA:2060-2082). Icol n, Irow m, T k x (n-k), S k x (m-k). */
+int rsvd_b200_id_two_sided_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q,
+                                    int s, uint64_t seed, double *Icol, double *Irow, double *T, rsvd_i64 ldt,
+                                    double *S, rsvd_i64 lds);
+/* cur_rand_decomp_fixed_rank (RRA:2191-2258). C m x k, U k x k, R k x n. */
+int rsvd_b200_cur_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q, int s,
+                           uint64_t seed, double *C, rsvd_i64 ldc, double *U, rsvd_i64 ldu, double *R, rsvd_i64 ldr);
+/* streamed 100*||A - U diag(S) V^T||_F/||A||_F (get_percent_error_between_two_mats after form_svd_product_matrix,
+ * MVF:391-405,1304-1318) without forming the dense m x n product at once. */
+double rsvd_b200_svd_percent_error_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, const double *U, rsvd_i64 ldu,
+                                       const double *S, const double *V, rsvd_i64 ldv, rsvd_i64 k);
+
+/* ---- row-partitioned multi-GPU (one process per GPU; A_g = rows of this rank) ------------------------- */
+/* NCCL is used only for the sums of n x l products and l x l Gram matrices. */
+int rsvd_b200_comm_unique_id(char id_out[128]);
+int rsvd_b200_comm_init(int rank, int world, const char id[128]);
+void rsvd_b200_comm_destroy(void);
+int rsvd_b200_allreduce_sum(double *d, rsvd_i64 count);
+/* even row split used by the drivers: rows [*row0, *row0 + *rows) of an m-row matrix for `rank` of `world`. */
+void rsvd_b200_row_partition(rsvd_i64 m, int world, int rank, rsvd_i64 *row0, rsvd_i64 *rows);
+
+/* ---- measurement helpers ------------------------------------------------------------------------------ */
+/* register-resident DMMA (use_dfma = 0) or DFMA (1) loop: measured FP64 peak of this GPU in TFLOP/s. */
+double rsvd_b200_fp64_peak_tflops(int iters, int use_dfma);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSVD_B200_H */

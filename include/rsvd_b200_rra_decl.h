@@ -1,0 +1,49 @@
+/* rsvd_b200_rra_decl.h — declarations behind the drop-in header rank_revealing_algorithms_intel_mkl.h
+ * (reference: multi_core_mkl_code/rank_revealing_algorithms_intel_mkl.h:3-110 and the _64bit twin).
+ * The randomized range-finder / QB hot path is implemented on the B200 (sm_100a); see SURVEY.md §8a. */
+#ifndef RSVD_B200_RRA_DECL_H
+#define RSVD_B200_RRA_DECL_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- randomized SVD (RRH:5-8) ---- */
+void low_rank_svd_rand_decomp_fixed_rank(mat *M, RSVD_INT k, RSVD_INT p, RSVD_INT vnum, RSVD_INT q, RSVD_INT s,
+                                         RSVD_INT *frank, mat **U, mat **S, mat **V);
+void low_rank_svd_blockrand_decomp_fixed_rank_or_prec(mat *M, RSVD_INT k, RSVD_INT p, double TOL, RSVD_INT vnum,
+                                                      RSVD_INT kstep, RSVD_INT q, RSVD_INT s, RSVD_INT *frank,
+                                                      mat **U, mat **S, mat **V);
+
+/* ---- blocked randQB with power scheme (RRH:60) ---- */
+void randQB_pb_new(mat *M, RSVD_INT kstep, RSVD_INT nstep, double TOL, RSVD_INT q, RSVD_INT s, RSVD_INT *frank,
+                   mat **Q, mat **B);
+
+/* ---- pivoted QR through the dgeqp3-compatible device kernel (RRH:40) ---- */
+void pivotedQR_mkl(mat *M, mat **Q, mat **R, vec **I);
+
+/* ---- interpolative decompositions (RRH:65-78) ---- */
+void id_decomp_fixed_rank_or_prec(mat *M, RSVD_INT k, double TOL, RSVD_INT *frank, vec **I, mat **T);
+void id_rand_decomp_fixed_rank(mat *M, RSVD_INT k, RSVD_INT p, RSVD_INT q, RSVD_INT s, vec **I, mat **T);
+void id_two_sided_rand_decomp_fixed_rank(mat *M, RSVD_INT k, RSVD_INT p, RSVD_INT q, RSVD_INT s, vec **Icol,
+                                         vec **Irow, mat **T, mat **S);
+
+/* ---- CUR (RRH:88) ---- */
+void cur_rand_decomp_fixed_rank(mat *M, RSVD_INT k, RSVD_INT p, RSVD_INT q, RSVD_INT s, mat **C, mat **U, mat **R);
+
+/* ---- evaluation helpers used by every driver (RRH:95-110): print 100*||M - approx||_F/||M||_F ---- */
+void use_low_rank_svd_for_approximation(mat *M, mat *U, mat *S, mat *V);
+void use_QB_decomp_for_approximation(mat *M, mat *Q, mat *B);
+void use_id_decomp_for_approximation(mat *M, mat *T, vec *I, RSVD_INT k);
+void use_id_two_sided_decomp_for_approximation(mat *M, mat *T, mat *S, vec *Icol, vec *Irow, RSVD_INT k);
+void use_cur_decomp_for_approximation(mat *M, mat *C, mat *U, mat *R);
+
+/* ---- out-of-band status (the reference API is void and unchecked) ---- */
+int rsvd_b200_api_status(void);                 /* 0 = last call succeeded */
+const char *rsvd_b200_api_last_error(void);
+double rsvd_b200_api_last_percent_error(void);  /* value printed by the last use_*_for_approximation call */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

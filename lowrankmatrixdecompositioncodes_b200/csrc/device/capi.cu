@@ -1,0 +1,168 @@
+// capi.cu — extern "C" surface of the device layer (declared in include/rsvd_b200.h).
+#include "common.cuh"
+
+namespace rsvd {
+int svd_from_q(const double *A, i64 m, i64 n, i64 lda, double *Q, i64 ldq, i64 l, i64 k, int vnum, double *U, i64 ldu,
+               double *S, double *V, i64 ldv);
+int svd_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int vnum, int q, int s, uint64_t seed,
+             const double *omega, double *U, i64 ldu, double *S, double *V, i64 ldv);
+int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, int q, int s, uint64_t seed, double *Q,
+           i64 ldq, double *B, i64 ldb, i64 max_rank, i64 *frank_out);
+int id_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, const double *omega,
+            double *I, double *T, i64 ldt);
+int id_full(const double *M, i64 k, i64 n, i64 ldm, double *I, double *T, i64 ldt);
+int id_two_sided_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, double *Icol,
+                      double *Irow, double *T, i64 ldt, double *S, i64 lds, i64 m_global);
+int cur_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, double *Cm, i64 ldc,
+             double *U, i64 ldu, double *R, i64 ldr, i64 m_global);
+double svd_percent_error(const double *A, i64 m, i64 n, i64 lda, const double *U, i64 ldu, const double *S,
+                         const double *V, i64 ldv, i64 k);
+}  // namespace rsvd
+
+using namespace rsvd;
+
+#define READY()            \
+    do {                   \
+        ensure_init();     \
+        if (!ctx().inited) return 1; \
+    } while (0)
+
+static i64 global_rows(i64 m_local) {
+    // in a row partition the option "m_global" carries the total row count; default = local
+    return (ctx().world > 1 && ctx().m_global > 0) ? (i64)ctx().m_global : m_local;
+}
+
+extern "C" {
+
+int rsvd_b200_gemm(char ta, char tb, rsvd_i64 m, rsvd_i64 n, rsvd_i64 k, double alpha, const double *A, rsvd_i64 lda,
+                   const double *B, rsvd_i64 ldb, double beta, double *C, rsvd_i64 ldc) {
+    READY();
+    Gemm g;
+    g.ta = ta; g.tb = tb; g.m = m; g.n = n; g.k = k; g.alpha = alpha; g.beta = beta;
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    gemm(g);
+    return g_status;
+}
+
+int rsvd_b200_sketch(char ta, rsvd_i64 m, rsvd_i64 n, rsvd_i64 k, const double *A, rsvd_i64 lda, uint64_t seed,
+                     rsvd_i64 sk, rsvd_i64 sc, rsvd_i64 off, double *C, rsvd_i64 ldc) {
+    READY();
+    Gemm g;
+    g.ta = ta; g.tb = 'N'; g.m = m; g.n = n; g.k = k; g.A = A; g.lda = lda; g.C = C; g.ldc = ldc;
+    g.philox = true; g.seed = seed; g.ph_sk = sk; g.ph_sc = sc; g.ph_off = off;
+    gemm(g);
+    return g_status;
+}
+
+int rsvd_b200_fill_normal(double *d, rsvd_i64 n, uint64_t seed, rsvd_i64 first) {
+    READY();
+    fill_normal(d, n, seed, first);
+    return g_status;
+}
+
+int rsvd_b200_orthonormalize(double *Y, rsvd_i64 ldy, rsvd_i64 m, rsvd_i64 l, double *R, rsvd_i64 ldr) {
+    READY();
+    if (l > m && ctx().world == 1) { set_error("rsvd_b200_orthonormalize: need m >= l (got %lld x %lld)", (long long)m, (long long)l); return 1; }
+    orthonormalize(Y, ldy, m, l, R, ldr, true);
+    return g_status;
+}
+
+int rsvd_b200_geqp3(double *A, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n, double *jpvt) {
+    READY();
+    geqp3(A, lda, m, n, jpvt);
+    return g_status;
+}
+
+int rsvd_b200_svd_small(double *A, rsvd_i64 lda, rsvd_i64 n, double *U, rsvd_i64 ldu, double *s, double *Vt, rsvd_i64 ldvt) {
+    READY();
+    jacobi_svd(A, lda, n, U, ldu, s, Vt, ldvt);
+    return g_status;
+}
+
+int rsvd_b200_eig_small(double *A, rsvd_i64 lda, rsvd_i64 n, double *w) {
+    READY();
+    jacobi_eig(A, lda, n, w);
+    return g_status;
+}
+
+int rsvd_b200_trsm_left_upper(const double *R, rsvd_i64 ldr, rsvd_i64 k, double *B, rsvd_i64 ldb, rsvd_i64 ncols) {
+    READY();
+    trsm_left_upper(R, ldr, k, B, ldb, ncols);
+    return g_status;
+}
+
+int rsvd_b200_lu_solve(double *A, rsvd_i64 lda, rsvd_i64 n, double *B, rsvd_i64 ldb, rsvd_i64 nrhs) {
+    READY();
+    int info = lu_solve(A, lda, n, B, ldb, nrhs);
+    if (info) set_error("rsvd_b200_lu_solve: zero pivot at column %d", info);
+    return g_status;
+}
+
+double rsvd_b200_frob_norm(const double *A, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n) {
+    ensure_init();
+    if (!ctx().inited) return -1.0;
+    return frob_norm(A, lda, m, n);
+}
+
+int rsvd_b200_transpose(const double *A, rsvd_i64 lda, double *B, rsvd_i64 ldb, rsvd_i64 m, rsvd_i64 n) {
+    READY();
+    transpose(A, lda, B, ldb, m, n);
+    return g_status;
+}
+
+int rsvd_b200_svd_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int vnum, int q,
+                           int s, uint64_t seed, const double *omega, double *U, rsvd_i64 ldu, double *S, double *V,
+                           rsvd_i64 ldv) {
+    READY();
+    return svd_rand(A, m, n, lda, k, p, vnum, q, s, seed, omega, U, ldu, S, V, ldv);
+}
+
+int rsvd_b200_randqb_dev(double *Awork, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 kstep, rsvd_i64 nstep, double tol,
+                         int q, int s, uint64_t seed, double *Q, rsvd_i64 ldq, double *B, rsvd_i64 ldb, rsvd_i64 *frank) {
+    READY();
+    // capacity of Q/B in columns/rows: ldb rows of B were allocated by the caller
+    return randqb(Awork, m, n, lda, kstep, nstep, tol, q, s, seed, Q, ldq, B, ldb, ldb, frank);
+}
+
+int rsvd_b200_svd_from_q_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, double *Q, rsvd_i64 ldq, rsvd_i64 l,
+                             rsvd_i64 k, int vnum, double *U, rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv) {
+    READY();
+    return svd_from_q(A, m, n, lda, Q, ldq, l, k, vnum, U, ldu, S, V, ldv);
+}
+
+int rsvd_b200_id_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q, int s,
+                          uint64_t seed, const double *omega, double *I, double *T, rsvd_i64 ldt) {
+    READY();
+    return id_rand(A, m, n, lda, k, p, q, s, seed, omega, I, T, ldt);
+}
+
+int rsvd_b200_id_full_dev(const double *M, rsvd_i64 k, rsvd_i64 n, rsvd_i64 ldm, double *I, double *T, rsvd_i64 ldt) {
+    READY();
+    return id_full(M, k, n, ldm, I, T, ldt);
+}
+
+int rsvd_b200_id_two_sided_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q,
+                                    int s, uint64_t seed, double *Icol, double *Irow, double *T, rsvd_i64 ldt, double *S,
+                                    rsvd_i64 lds) {
+    READY();
+    return id_two_sided_rand(A, m, n, lda, k, p, q, s, seed, Icol, Irow, T, ldt, S, lds, global_rows(m));
+}
+
+int rsvd_b200_cur_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q, int s,
+                           uint64_t seed, double *C, rsvd_i64 ldc, double *U, rsvd_i64 ldu, double *R, rsvd_i64 ldr) {
+    READY();
+    return cur_rand(A, m, n, lda, k, p, q, s, seed, C, ldc, U, ldu, R, ldr, global_rows(m));
+}
+
+double rsvd_b200_svd_percent_error_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, const double *U, rsvd_i64 ldu,
+                                       const double *S, const double *V, rsvd_i64 ldv, rsvd_i64 k) {
+    return svd_percent_error(A, m, n, lda, U, ldu, S, V, ldv, k);
+}
+
+double rsvd_b200_fp64_peak_tflops(int iters, int use_dfma) {
+    ensure_init();
+    if (!ctx().inited) return -1.0;
+    return dmma_peak_tflops(iters, use_dfma);
+}
+
+}  // extern "C"

@@ -1,0 +1,295 @@
+// cholqr.cu — re-orthonormalisation of tall-skinny panels: CholeskyQR2 with an l x l Gram matrix, and a
+// TSQR(R)-preconditioned fallback when the Gram matrix is too ill-conditioned for Cholesky.
+// Replaces QR_factorization_getQ / compact_QR_factorization (dgeqrf + dorgqr Householder QR,
+// matrix_vector_functions_intel_mkl.c:1251-1263, 1214-1245) as called from RRA:106,118,130,146,1655,1673,1690,1722,
+// 1892,1915.  The basis differs from LAPACK's by an l x l orthogonal factor (signs of R's diagonal are positive
+// here); everything downstream on the hot path is invariant under that (SURVEY.md §7 hard part 3).
+//
+// Row-partitioned multi-GPU: the only communication is the allreduce of the l x l Gram matrix (twice).
+#include "common.cuh"
+
+namespace rsvd {
+
+constexpr int PB = 64;   // Cholesky / inverse block size
+
+// ---- blocked upper Cholesky G = R^T R ------------------------------------------------------------------
+// factor the diagonal block in shared memory (one CTA); flag = failing column + 1 on a non-positive pivot
+__global__ void __launch_bounds__(PB * 4) potf2_kernel(double *G, i64 ldg, i64 j0, int jb, int *flag) {
+    __shared__ double S[PB][PB + 1];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < PB * PB; e += blockDim.x) {
+        int i = e % PB, j = e / PB;
+        S[i][j] = (i < jb && j < jb && i <= j) ? G[(j0 + j) * ldg + j0 + i] : 0.0;
+    }
+    __syncthreads();
+    for (int c = 0; c < jb; ++c) {
+        // R(c,c) = sqrt(G(c,c) - sum_{r<c} R(r,c)^2): the sums were already subtracted (right-looking inside the block)
+        double d = S[c][c];
+        if (!(d > 0.0)) {
+            if (tid == 0) atomicCAS(flag, 0, (int)(j0 + c + 1));
+            d = 1.0;   // keep going with finite numbers; the caller discards the result
+        }
+        double r = sqrt(d);
+        __syncthreads();
+        if (tid == 0) S[c][c] = r;
+        for (int j = c + 1 + tid; j < jb; j += blockDim.x) S[c][j] /= r;
+        __syncthreads();
+        // trailing update of the block: S(i,j) -= R(c,i) R(c,j), i<=j, i>c
+        int nrem = jb - c - 1;
+        for (int e = tid; e < nrem * nrem; e += blockDim.x) {
+            int i = c + 1 + e % nrem, j = c + 1 + e / nrem;
+            if (i <= j) S[i][j] -= S[c][i] * S[c][j];
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < PB * PB; e += blockDim.x) {
+        int i = e % PB, j = e / PB;
+        if (i < jb && j < jb) G[(j0 + j) * ldg + j0 + i] = (i <= j) ? S[i][j] : 0.0;
+    }
+}
+
+// row panel: G(j0:j0+jb, c) <- R_jj^{-T} G(j0:j0+jb, c) for c >= j0+jb  (forward substitution, one column per thread)
+__global__ void __launch_bounds__(128) potrf_panel_kernel(double *G, i64 ldg, i64 n, i64 j0, int jb) {
+    __shared__ double S[PB][PB + 1];
+    for (int e = threadIdx.x; e < PB * PB; e += blockDim.x) {
+        int i = e % PB, j = e / PB;
+        S[i][j] = (i < jb && j < jb && i <= j) ? G[(j0 + j) * ldg + j0 + i] : 0.0;
+    }
+    __syncthreads();
+    i64 c = j0 + jb + (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double x[PB];
+    double *col = G + c * ldg + j0;
+#pragma unroll 1
+    for (int i = 0; i < jb; ++i) {
+        double s = col[i];
+        for (int r = 0; r < i; ++r) s -= S[r][i] * x[r];
+        x[i] = s / S[i][i];
+    }
+    for (int i = 0; i < jb; ++i) col[i] = x[i];
+}
+
+int potrf_upper(double *G, i64 ldg, i64 n) {
+    ensure_init();
+    int *flag = ctx().d_flag;
+    RSVD_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx().stream));
+    for (i64 j0 = 0; j0 < n; j0 += PB) {
+        int jb = (int)min((i64)PB, n - j0);
+        potf2_kernel<<<1, PB * 4, 0, ctx().stream>>>(G, ldg, j0, jb, flag);
+        count_launch();
+        i64 rest = n - j0 - jb;
+        if (rest > 0) {
+            potrf_panel_kernel<<<(unsigned)((rest + 127) / 128), 128, 0, ctx().stream>>>(G, ldg, n, j0, jb);
+            count_launch();
+            Gemm g;   // G22 -= R12^T R12
+            g.ta = 'T'; g.tb = 'N'; g.m = rest; g.n = rest; g.k = jb; g.alpha = -1.0; g.beta = 1.0;
+            g.A = G + (j0 + jb) * ldg + j0; g.lda = ldg; g.B = g.A; g.ldb = ldg;
+            g.C = G + (j0 + jb) * ldg + j0 + jb; g.ldc = ldg;
+            gemm(g);
+        }
+    }
+    keep_upper(G, ldg, n);
+    RSVD_CUDA(cudaMemcpyAsync(ctx().h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    RSVD_CUDA(cudaStreamSynchronize(ctx().stream));
+    return ctx().h_flag[0];
+}
+
+// ---- inverse of an upper-triangular matrix by recursive doubling -------------------------------------------
+// diagonal PB x PB blocks: thread j back-substitutes column j of the inverse
+__global__ void __launch_bounds__(PB) trtri_diag_kernel(const double *__restrict__ R, i64 ldr, i64 n, double *__restrict__ X, i64 ldx) {
+    __shared__ double S[PB][PB + 1];
+    const i64 o = (i64)blockIdx.x * PB;
+    const int nb = (int)min((i64)PB, n - o);
+    for (int e = threadIdx.x; e < PB * PB; e += blockDim.x) {
+        int i = e % PB, j = e / PB;
+        S[i][j] = (i < nb && j < nb && i <= j) ? R[(o + j) * ldr + o + i] : (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const int j = threadIdx.x;
+    if (j >= nb) return;
+    double x[PB];
+#pragma unroll 1
+    for (int i = j; i >= 0; --i) {
+        double s = (i == j) ? 1.0 : 0.0;
+        for (int l = i + 1; l <= j; ++l) s -= S[i][l] * x[l];
+        x[i] = s / S[i][i];
+    }
+    for (int i = 0; i <= j; ++i) X[(o + j) * ldx + o + i] = x[i];
+}
+
+void trtri_upper(const double *R, i64 ldr, i64 n, double *X, i64 ldx) {
+    ensure_init();
+    if (n <= 0) return;
+    // X = 0, then diagonal blocks
+    RSVD_CUDA(cudaMemset2DAsync(X, (size_t)ldx * 8, 0, (size_t)n * 8, (size_t)n, ctx().stream));
+    int nblk = (int)((n + PB - 1) / PB);
+    trtri_diag_kernel<<<nblk, PB, 0, ctx().stream>>>(R, ldr, n, X, ldx);
+    count_launch();
+    DBuf tmp((size_t)n * n);
+    // level s: merge [X11 ?; 0 X22] of sizes (s, r): X12 = -X11 * R12 * X22
+    for (i64 s = PB; s < n; s *= 2) {
+        i64 npairs_full = n / (2 * s);                 // pairs with two full blocks
+        i64 tail0 = npairs_full * 2 * s;               // start of a possibly partial pair
+        i64 tail_r = (n - tail0 > s) ? (n - tail0 - s) : 0;   // size of the partial second block
+        // T = R12 * X22   (s x r)
+        if (npairs_full > 0) {
+            Gemm g;
+            g.ta = 'N'; g.tb = 'N'; g.m = s; g.n = s; g.k = s;
+            g.A = R + s * ldr; g.lda = ldr; g.sA = 2 * s * (ldr + 1);
+            g.B = X + s * ldx + s; g.ldb = ldx; g.sB = 2 * s * (ldx + 1);
+            g.C = tmp.p; g.ldc = s; g.sC = s * s; g.batch = (int)npairs_full;
+            gemm(g);
+            Gemm h;
+            h.ta = 'N'; h.tb = 'N'; h.m = s; h.n = s; h.k = s; h.alpha = -1.0;
+            h.A = X; h.lda = ldx; h.sA = 2 * s * (ldx + 1);
+            h.B = tmp.p; h.ldb = s; h.sB = s * s;
+            h.C = X + s * ldx; h.ldc = ldx; h.sC = 2 * s * (ldx + 1); h.batch = (int)npairs_full;
+            gemm(h);
+        }
+        if (tail_r > 0) {
+            const double *R12 = R + (tail0 + s) * ldr + tail0;
+            double *X11 = X + tail0 * ldx + tail0, *X22 = X + (tail0 + s) * ldx + tail0 + s, *X12 = X + (tail0 + s) * ldx + tail0;
+            Gemm g;
+            g.ta = 'N'; g.tb = 'N'; g.m = s; g.n = tail_r; g.k = tail_r; g.A = R12; g.lda = ldr; g.B = X22; g.ldb = ldx;
+            g.C = tmp.p; g.ldc = s;
+            gemm(g);
+            Gemm h;
+            h.ta = 'N'; h.tb = 'N'; h.m = s; h.n = tail_r; h.k = s; h.alpha = -1.0; h.A = X11; h.lda = ldx; h.B = tmp.p; h.ldb = s;
+            h.C = X12; h.ldc = ldx;
+            gemm(h);
+        }
+    }
+}
+
+// ---- diagonal statistics of R: out[0] = min diag, out[1] = max diag --------------------------------------------
+__global__ void diag_minmax_kernel(const double *R, i64 ldr, i64 n, double *out) {
+    __shared__ double smin[32], smax[32];
+    double mn = INFINITY, mx = 0.0;
+    for (i64 i = threadIdx.x; i < n; i += blockDim.x) {
+        double d = fabs(R[i * ldr + i]);
+        if (!(d == d)) d = 0.0;   // NaN -> treat as breakdown
+        mn = fmin(mn, d); mx = fmax(mx, d);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mn = fmin(mn, smin[w]); mx = fmax(mx, smax[w]); }
+        out[0] = mn; out[1] = mx;
+    }
+}
+
+// One Cholesky-QR pass: Qout = Yin * chol(Yin^T Yin)^{-1}.  Returns 0 ok, 1 = Gram not safely factorable.
+// Rout (l x l) receives the Cholesky factor.  cond_limit: reject when max/min of diag(R) exceeds it.
+static int cholqr_pass(const double *Yin, i64 ldy, i64 m, i64 l, double *Qout, i64 ldq, double *Rout, double cond_limit, bool sharded) {
+    DBuf G((size_t)l * l), Rinv((size_t)l * l), stat(2);
+    Gemm g;   // Gram = Yin^T Yin
+    g.ta = 'T'; g.tb = 'N'; g.m = l; g.n = l; g.k = m; g.A = Yin; g.lda = ldy; g.B = Yin; g.ldb = ldy; g.C = G.p; g.ldc = l;
+    gemm(g);
+    if (sharded) allreduce_sum(G.p, (size_t)l * l);
+    int info = potrf_upper(G.p, l, l);
+    if (info != 0) return 1;
+    diag_minmax_kernel<<<1, 256, 0, ctx().stream>>>(G.p, l, l, stat.p);
+    count_launch();
+    double h[2];
+    RSVD_CUDA(cudaMemcpyAsync(h, stat.p, 16, cudaMemcpyDeviceToHost, ctx().stream));
+    RSVD_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (!(h[0] > 0.0) || h[1] / h[0] > cond_limit) return 1;
+    trtri_upper(G.p, l, l, Rinv.p, l);
+    Gemm q;   // Qout = Yin * Rinv
+    q.ta = 'N'; q.tb = 'N'; q.m = m; q.n = l; q.k = l; q.A = Yin; q.lda = ldy; q.B = Rinv.p; q.ldb = l; q.C = Qout; q.ldc = ldq;
+    gemm(q);
+    if (Rout) copy_matrix(G.p, l, Rout, l, l, l);
+    return 0;
+}
+
+// R3 = R2 * R1 (upper * upper), result in R1buf
+static void accumulate_r(double *R2, double *R1, i64 l) {
+    DBuf T((size_t)l * l);
+    Gemm g;
+    g.ta = 'N'; g.tb = 'N'; g.m = l; g.n = l; g.k = l; g.A = R2; g.lda = l; g.B = R1; g.ldb = l; g.C = T.p; g.ldc = l;
+    gemm(g);
+    copy_matrix(T.p, l, R1, l, l, l);
+}
+
+// TSQR(R) fallback: Householder R of the local row block (no squaring of the condition number), stacked over the
+// ranks and factored again; then Q1 = Y R^{-1} has cond(Q1) = O(1 + eps*cond(Y)) and one Cholesky-QR pass finishes.
+static int tsqr_r(const double *Y, i64 ldy, i64 m, i64 l, double *R /* l x l */, bool sharded) {
+    Ctx &c = ctx();
+    // local Householder R.  Row blocks shorter than l are padded with zero rows.
+    i64 mm = max(m, l);
+    DBuf W((size_t)mm * l);
+    if (mm > m) set_zero(W.p, (size_t)mm * l);
+    copy_matrix(Y, ldy, W.p, mm, m, l);
+    geqrf_r(W.p, mm, mm, l);
+    if (c.world == 1 || !sharded) {
+        copy_matrix(W.p, mm, R, l, l, l);
+        keep_upper(R, l, l);
+        return 0;
+    }
+    // stack the world's R factors (allgather emulated by a zero-padded sum), factor the (world*l) x l stack
+    i64 rows = (i64)c.world * l;
+    DBuf S((size_t)rows * l);
+    set_zero(S.p, (size_t)rows * l);
+    copy_matrix(W.p, mm, S.p + (i64)c.rank * l, rows, l, l);
+    // zero the strictly-lower part of this rank's slot (Householder vectors live there)
+    {
+        DBuf T((size_t)l * l);
+        copy_matrix(S.p + (i64)c.rank * l, rows, T.p, l, l, l);
+        keep_upper(T.p, l, l);
+        copy_matrix(T.p, l, S.p + (i64)c.rank * l, rows, l, l);
+    }
+    allreduce_sum(S.p, (size_t)rows * l);
+    geqrf_r(S.p, rows, rows, l);
+    copy_matrix(S.p, rows, R, l, l, l);
+    keep_upper(R, l, l);
+    return 0;
+}
+
+void orthonormalize(double *Y, i64 ldy, i64 m, i64 l, double *R, i64 ldr, bool sharded) {
+    ensure_init();
+    if (m <= 0 || l <= 0) return;
+    Ctx &c = ctx();
+    DBuf Q1((size_t)m * l), R1((size_t)l * l), R2((size_t)l * l);
+    int bad = 1;
+    if (!c.force_qr_fallback) {
+        // CholeskyQR2: cond(Y) up to ~1e7 is safe (cond(Gram) = cond(Y)^2 must stay well below 1/eps)
+        bad = cholqr_pass(Y, ldy, m, l, Q1.p, m, R1.p, 1.0e7, sharded);
+        if (!bad) {
+            bad = cholqr_pass(Q1.p, m, m, l, Y, ldy, R2.p, 1.0e3, sharded);
+            if (!bad) c.last_qr_path = 1;
+        }
+    }
+    if (bad) {
+        // TSQR-preconditioned path
+        c.qr_fallbacks++;
+        c.last_qr_path = 2;
+        tsqr_r(Y, ldy, m, l, R1.p, sharded);
+        DBuf Rinv((size_t)l * l);
+        trtri_upper(R1.p, l, l, Rinv.p, l);
+        Gemm q;
+        q.ta = 'N'; q.tb = 'N'; q.m = m; q.n = l; q.k = l; q.A = Y; q.lda = ldy; q.B = Rinv.p; q.ldb = l; q.C = Q1.p; q.ldc = m;
+        gemm(q);
+        int b2 = cholqr_pass(Q1.p, m, m, l, Y, ldy, R2.p, 1.0e7, sharded);
+        if (b2) {
+            // numerically rank-deficient panel: one more preconditioned sweep on Q1 (its R is well scaled now)
+            DBuf R3((size_t)l * l), Q2((size_t)m * l);
+            tsqr_r(Q1.p, m, m, l, R3.p, sharded);
+            trtri_upper(R3.p, l, l, Rinv.p, l);
+            Gemm q2 = q; q2.A = Q1.p; q2.lda = m; q2.C = Q2.p; q2.ldc = m;
+            gemm(q2);
+            accumulate_r(R3.p, R1.p, l);
+            b2 = cholqr_pass(Q2.p, m, m, l, Y, ldy, R2.p, 1.0e12, sharded);
+            if (b2) { set_error("rsvd_b200: orthonormalisation failed (panel %lld x %lld is numerically singular)", (long long)m, (long long)l); return; }
+        }
+    }
+    if (R) {
+        accumulate_r(R2.p, R1.p, l);   // R = R2 * R1
+        copy_matrix(R1.p, l, R, ldr, l, l);
+    }
+}
+
+}  // namespace rsvd

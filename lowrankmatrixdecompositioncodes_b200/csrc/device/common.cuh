@@ -1,0 +1,132 @@
+// common.cuh — shared declarations of the device layer (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../../include/rsvd_b200.h"
+#include "../../../include/rsvd_b200_rng.h"
+
+namespace rsvd {
+
+typedef long long i64;
+
+// ---- error channel (the reference API is `void`; errors are reported out of band) -------------
+void set_error(const char *fmt, ...);
+extern int g_status;
+
+#define RSVD_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            rsvd::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+        }                                                                                    \
+    } while (0)
+
+// ---- context -----------------------------------------------------------------------------------
+struct Ctx {
+    int device = -1;
+    int sms = 148;
+    cudaStream_t stream = nullptr;   // compute stream (all kernels)
+    cudaStream_t copy_stream = nullptr;
+    bool inited = false;
+    int *d_flag = nullptr;           // device int[8] scratch for status flags
+    int *h_flag = nullptr;           // pinned mirror
+    // distributed (row partition): filled by rsvd_b200_comm_init
+    int rank = 0, world = 1;
+    long long m_global = 0;          // total rows of the row-partitioned matrix (0 = not partitioned)
+    long long row0 = 0;              // global index of this rank's first row (left sketches index Omega by global row)
+    void *nccl_comm = nullptr;
+    // statistics
+    unsigned long long launches = 0;
+    int verbose = 0;
+    int force_generic_gemm = 0;
+    int force_qr_fallback = 0;
+    int last_qr_path = 0;            // 1 = CholeskyQR2, 2 = TSQR-preconditioned fallback
+    unsigned long long qr_fallbacks = 0;
+};
+Ctx &ctx();
+void ensure_init();
+
+double *dalloc(size_t n_doubles);
+void *dalloc_bytes(size_t bytes);
+void dfree(void *p);
+inline void count_launch(int n = 1) { ctx().launches += (unsigned long long)n; }
+
+// RAII device buffer
+struct DBuf {
+    double *p = nullptr;
+    size_t n = 0;
+    DBuf() {}
+    explicit DBuf(size_t n_) : p(dalloc(n_)), n(n_) {}
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    DBuf(DBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DBuf &operator=(DBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    void alloc(size_t n_) { release(); p = dalloc(n_); n = n_; }
+    void release() { if (p) dfree(p); p = nullptr; n = 0; }
+    ~DBuf() { release(); }
+    operator double *() const { return p; }
+};
+
+// ---- GEMM engine (gemm.cu) ---------------------------------------------------------------------
+// C(m x n) = alpha * op(A)(m x k) * op(B)(k x n) + beta * C, column-major everywhere.
+// If `philox` is set, op(B)(kk, j) is not read from memory: it is normal(seed, ph_off + kk*ph_sk + j*ph_sc).
+struct Gemm {
+    char ta = 'N', tb = 'N';
+    i64 m = 0, n = 0, k = 0;
+    double alpha = 1.0, beta = 0.0;
+    const double *A = nullptr; i64 lda = 0;
+    const double *B = nullptr; i64 ldb = 0;
+    double *C = nullptr; i64 ldc = 0;
+    int batch = 1; i64 sA = 0, sB = 0, sC = 0;   // strided batch
+    bool philox = false; uint64_t seed = 0; i64 ph_sk = 0, ph_sc = 0, ph_off = 0;
+};
+void gemm(const Gemm &g);
+// which kernel family served the last gemm() call: 0 generic, 1 tma
+extern int g_last_gemm_path;
+double dmma_peak_tflops(int iters, int use_dfma);
+
+// ---- small kernels (small.cu) ------------------------------------------------------------------
+void transpose(const double *A, i64 lda, double *B, i64 ldb, i64 m, i64 n);   // B(n x m) = A(m x n)^T
+void copy_matrix(const double *A, i64 lda, double *B, i64 ldb, i64 m, i64 n);
+void set_zero(double *A, size_t n);
+void set_identity(double *A, i64 lda, i64 n);
+void keep_upper(double *A, i64 lda, i64 n);                                  // zero strictly-lower part
+void gather_cols(const double *A, i64 lda, i64 m, const double *idx, i64 k, double *B, i64 ldb);
+void gather_rows(const double *A, i64 lda, i64 n, const double *idx, i64 k, double *B, i64 ldb);
+void scale_cols(double *A, i64 lda, i64 m, i64 n, const double *s, int invert);
+double frob_norm(const double *A, i64 lda, i64 m, i64 n);                     // syncs
+void sumsq_async(const double *A, i64 lda, i64 m, i64 n, double *d_out);      // d_out[0] = sum of squares
+void fill_normal(double *A, i64 n_entries, uint64_t seed, i64 first);
+void trsm_left_upper(const double *R, i64 ldr, i64 k, double *B, i64 ldb, i64 ncols);  // B <- R^{-1} B
+int lu_solve(double *A, i64 lda, i64 n, double *B, i64 ldb, i64 nrhs);        // dgesv semantics, in place
+
+// ---- orthonormalisation (cholqr.cu) ------------------------------------------------------------
+// Q (m x l, ld) <- orthonormal basis of range(Y); in place. If R != nullptr also returns R (l x l upper).
+// sharded = true: Y is this rank's row block of a row-partitioned panel (Gram matrices are all-reduced);
+// sharded = false: Y is replicated on every rank (no communication).
+void orthonormalize(double *Y, i64 ldy, i64 m, i64 l, double *R, i64 ldr, bool sharded = true);
+int potrf_upper(double *G, i64 ldg, i64 n);       // in-place upper Cholesky G = R^T R; returns 0 or failing column+1
+void trtri_upper(const double *R, i64 ldr, i64 n, double *Rinv, i64 ldi); // Rinv = R^{-1}
+
+// ---- Householder QR family (geqp3.cu) ----------------------------------------------------------
+// In-place dgeqp3-compatible column-pivoted QR (R in the upper triangle, jpvt 0-based as doubles).
+void geqp3(double *A, i64 lda, i64 m, i64 n, double *jpvt_out);
+// unpivoted Householder, R only (upper triangle of A on exit), used by the TSQR fallback
+void geqrf_r(double *A, i64 lda, i64 m, i64 n);
+
+// ---- small dense eigen/SVD (jacobi.cu) ---------------------------------------------------------
+// A (n x n, overwritten) = U diag(s) V^T, s descending. U (n x n), Vt (n x n).
+void jacobi_svd(double *A, i64 lda, i64 n, double *U, i64 ldu, double *s, double *Vt, i64 ldvt);
+// symmetric eigendecomposition, ascending eigenvalues, eigenvectors in columns of A on exit
+void jacobi_eig(double *A, i64 lda, i64 n, double *w);
+
+// ---- collectives (dist.cu) ---------------------------------------------------------------------
+void allreduce_sum(double *d, size_t count);      // no-op when world == 1
+
+}  // namespace rsvd

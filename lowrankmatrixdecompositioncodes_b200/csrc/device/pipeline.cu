@@ -1,0 +1,338 @@
+// pipeline.cu — the device-resident algorithms: randomized SVD, blocked randQB with its on-device tolerance
+// test, randomized ID / two-sided ID / CUR.  A and every intermediate stay in HBM; the host only sequences
+// kernels and reads back 4-byte status flags.  Control flow follows the reference line by line (citations are
+// rank_revealing_algorithms_intel_mkl.c = RRA) so that results agree with it for the same Omega.
+//
+// Row partition (world > 1): `A` is this rank's block of rows; m is the local row count.  Products that contract
+// over rows (A^T * X) are all-reduced; n x l panels are replicated, m x l panels are row-sharded.
+#include "common.cuh"
+#include <vector>
+
+namespace rsvd {
+
+namespace {
+
+inline void mm(char ta, char tb, i64 m, i64 n, i64 k, double alpha, const double *A, i64 lda, const double *B, i64 ldb,
+               double beta, double *C, i64 ldc) {
+    Gemm g;
+    g.ta = ta; g.tb = tb; g.m = m; g.n = n; g.k = k; g.alpha = alpha; g.beta = beta;
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    gemm(g);
+}
+// C = op(A) * Omega, Omega(kk, j) = normal(seed, off + kk*sk + j*sc)
+inline void sketch(char ta, i64 m, i64 n, i64 k, const double *A, i64 lda, uint64_t seed, i64 sk, i64 sc, i64 off,
+                   double *C, i64 ldc) {
+    Gemm g;
+    g.ta = ta; g.tb = 'N'; g.m = m; g.n = n; g.k = k; g.A = A; g.lda = lda; g.B = nullptr; g.ldb = 0; g.C = C; g.ldc = ldc;
+    g.philox = true; g.seed = seed; g.ph_sk = sk; g.ph_sc = sc; g.ph_off = off;
+    gemm(g);
+}
+
+__global__ void sqrt_clamp_kernel(double *w, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = sqrt(fmax(w[i], 0.0));
+}
+
+// V(Icol[i], j) = (i < k) ? delta_ij : T(j, i-k)   — V = [I_k ; T^T](Icol^{-1}, :)   (RRA:2200-2219)
+__global__ void build_v_kernel(const double *Icol, const double *T, i64 ldt, i64 n, i64 k, double *V, i64 ldv) {
+    i64 total = n * k;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        i64 i = e % n, j = e / n;
+        i64 dst = (i64)Icol[i];
+        V[j * ldv + dst] = (i < k) ? (i == j ? 1.0 : 0.0) : T[(i - k) * ldt + j];
+    }
+}
+
+// rows of the global matrix owned by this rank: R(i, :) = A(Irow[i] - row0, :) if owned else 0
+__global__ void gather_rows_owned_kernel(const double *A, i64 lda, i64 mloc, i64 n, i64 row0, const double *idx, i64 k,
+                                         double *B, i64 ldb) {
+    i64 total = k * n;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        i64 i = e % k, j = e / k;
+        i64 r = (i64)idx[i] - row0;
+        B[j * ldb + i] = (r >= 0 && r < mloc) ? A[j * lda + r] : 0.0;
+    }
+}
+
+// device-side tolerance test of randQB_pb_new (RRA:1771-1777): done = (sqrt(sumsq) < tol)
+__global__ void tol_check_kernel(const double *sumsq, double tol, int *done, double *norm_out) {
+    double nv = sqrt(sumsq[0]);
+    norm_out[0] = nv;
+    done[0] = (nv < tol) ? 1 : 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// SVD tail (RRA:133-225 and RRA:289-380)
+// ---------------------------------------------------------------------------------------------------------
+int svd_from_q(const double *A, i64 m, i64 n, i64 lda, double *Q, i64 ldq, i64 l, i64 k, int vnum,
+               double *U, i64 ldu, double *S, double *V, i64 ldv) {
+    Ctx &c = ctx();
+    DBuf Bt((size_t)n * l);
+    mm('T', 'N', n, l, m, 1.0, A, lda, Q, ldq, 0.0, Bt.p, n);          // Bt = A^T Q   (RRA:139)  — last pass over A
+    allreduce_sum(Bt.p, (size_t)n * l);
+    if (vnum == 1 || vnum > 2) {
+        DBuf Rhat((size_t)l * l), Uhat((size_t)l * l), Vhat_t((size_t)l * l), Vhat((size_t)l * l), sv((size_t)l);
+        orthonormalize(Bt.p, n, n, l, Rhat.p, l, /*sharded=*/false);      // [Qhat, Rhat] = qr(Bt)  (RRA:146); Qhat overwrites Bt
+        jacobi_svd(Rhat.p, l, l, Uhat.p, l, sv.p, Vhat_t.p, l);           // Rhat = Uhat S Vhat^T   (RRA:152)
+        transpose(Vhat_t.p, l, Vhat.p, l, l, l);
+        mm('N', 'N', m, k, l, 1.0, Q, ldq, Vhat.p, l, 0.0, U, ldu);       // U = Q Vhat, first k columns (RRA:156,171)
+        mm('N', 'N', n, k, l, 1.0, Bt.p, n, Uhat.p, l, 0.0, V, ldv);      // V = Qhat Uhat          (RRA:160,172)
+        copy_matrix(sv.p, l, S, k, k, 1);
+    } else {
+        // eig of B B^T (RRA:175-225): B = Q^T A = Bt^T, so B B^T = Bt^T Bt
+        DBuf BBt((size_t)l * l), w((size_t)l), X((size_t)l * k);
+        mm('T', 'N', l, l, n, 1.0, Bt.p, n, Bt.p, n, 0.0, BBt.p, l);
+        jacobi_eig(BBt.p, l, l, w.p);                                     // ascending (RRA:190)
+        sqrt_clamp_kernel<<<(unsigned)((l + 127) / 128), 128, 0, c.stream>>>(w.p, (int)l);   // RRA:196-198
+        count_launch();
+        const double *Uk = BBt.p + (l - k) * l;                           // keep the LAST k (RRA:220-223)
+        mm('N', 'N', m, k, l, 1.0, Q, ldq, Uk, l, 0.0, U, ldu);           // U = Q Uhat             (RRA:203)
+        copy_matrix(Uk, l, X.p, l, l, k);
+        scale_cols(X.p, l, l, k, w.p + (l - k), 1);                       // Uhat S^{-1}            (RRA:208-211)
+        mm('N', 'N', n, k, l, 1.0, Bt.p, n, X.p, l, 0.0, V, ldv);         // V = B^T Uhat S^{-1}    (RRA:212)
+        copy_matrix(w.p + (l - k), k, S, k, k, 1);
+    }
+    return g_status;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// low_rank_svd_rand_decomp_fixed_rank (RRA:73-234)
+// ---------------------------------------------------------------------------------------------------------
+int svd_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int vnum, int q, int s, uint64_t seed,
+             const double *omega, double *U, i64 ldu, double *S, double *V, i64 ldv) {
+    ensure_init();
+    if (!ctx().inited) return 1;
+    const i64 l = k + p;
+    if (k <= 0 || p < 0 || l > n || s <= 0) { set_error("rsvd_b200: invalid parameters k=%lld p=%lld s=%d (need 0 < k+p <= n, s > 0)", (long long)k, (long long)p, s); return 1; }
+    DBuf Y((size_t)m * l), Z((size_t)n * l);
+    if (omega) mm('N', 'N', m, l, n, 1.0, A, lda, omega, n, 0.0, Y.p, m);           // Y = M RN (RRA:95)
+    else sketch('N', m, l, n, A, lda, seed, 1, n, 0, Y.p, m);                       // RN generated in the B-operand producer
+    for (int j = 1; j < q; ++j) {                                                   // NOTE j < q (RRA:101)
+        if ((2 * j - 2) % s == 0) orthonormalize(Y.p, m, m, l, nullptr, 0, true);   // RRA:106
+        mm('T', 'N', n, l, m, 1.0, A, lda, Y.p, m, 0.0, Z.p, n);                    // Z = M^T Y (RRA:108/112)
+        allreduce_sum(Z.p, (size_t)n * l);
+        if ((2 * j - 1) % s == 0) orthonormalize(Z.p, n, n, l, nullptr, 0, false);  // RRA:118
+        mm('N', 'N', m, l, n, 1.0, A, lda, Z.p, n, 0.0, Y.p, m);                    // Y = M Z (RRA:120/124)
+    }
+    Z.release();
+    orthonormalize(Y.p, m, m, l, nullptr, 0, true);                                 // Q (RRA:129-130)
+    return svd_from_q(A, m, n, lda, Y.p, m, l, k, vnum, U, ldu, S, V, ldv);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// randQB_pb_new (RRA:1576-1801)
+// ---------------------------------------------------------------------------------------------------------
+int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, int q, int s, uint64_t seed,
+           double *Q, i64 ldq, double *B, i64 ldb, i64 max_rank, i64 *frank_out) {
+    ensure_init();
+    Ctx &c = ctx();
+    if (!c.inited) return 1;
+    if (kstep <= 0 || s <= 0) { set_error("rsvd_b200: invalid kstep/s"); return 1; }
+    const bool tolMode = nstep <= 0;
+    if (tolMode) nstep = max_rank / kstep;
+    if (kstep * nstep > max_rank) nstep = max_rank / kstep;
+    DBuf Yp((size_t)m * kstep), W((size_t)n * kstep), sums(2);
+    int *done = c.d_flag + 24;
+    i64 frank = 0;
+    for (i64 step = 0; step < nstep; ++step) {                                      // RRA:1635
+        const i64 c0 = kstep * step;
+        sketch('N', m, kstep, n, A, lda, seed, 1, n, c0 * n, Yp.p, m);              // Yp = A RN(:,block) (RRA:1643-1644)
+        for (int j = 1; j <= q; ++j) {                                              // NOTE j <= q (RRA:1652)
+            if ((2 * j - 2) % s == 0) orthonormalize(Yp.p, m, m, kstep, nullptr, 0, true);   // RRA:1655
+            mm('T', 'N', n, kstep, m, 1.0, A, lda, Yp.p, m, 0.0, W.p, n);           // AtQp (RRA:1657-1658 / 1665)
+            allreduce_sum(W.p, (size_t)n * kstep);
+            if ((2 * j - 1) % s == 0) orthonormalize(W.p, n, n, kstep, nullptr, 0, false);   // RRA:1673
+            mm('N', 'N', m, kstep, n, 1.0, A, lda, W.p, n, 0.0, Yp.p, m);           // Yp = A AtQp2 (RRA:1674 / 1681)
+        }
+        orthonormalize(Yp.p, m, m, kstep, nullptr, 0, true);                        // Qp (RRA:1690)
+        if (step > 0 && step % 2 == 0) {                                            // RRA:1703-1722
+            DBuf T((size_t)c0 * kstep);
+            mm('T', 'N', c0, kstep, m, 1.0, Q, ldq, Yp.p, m, 0.0, T.p, c0);
+            allreduce_sum(T.p, (size_t)c0 * kstep);
+            mm('N', 'N', m, kstep, c0, -1.0, Q, ldq, T.p, c0, 1.0, Yp.p, m);
+            orthonormalize(Yp.p, m, m, kstep, nullptr, 0, true);
+        }
+        double *Bp = B + c0;                                                        // B(block,:) (RRA:1761)
+        mm('T', 'N', kstep, n, m, 1.0, Yp.p, m, A, lda, 0.0, Bp, ldb);              // Bp = Qp^T A (RRA:1741)
+        if (c.world > 1) {
+            DBuf t((size_t)kstep * n);
+            copy_matrix(Bp, ldb, t.p, kstep, kstep, n);
+            allreduce_sum(t.p, (size_t)kstep * n);
+            copy_matrix(t.p, kstep, Bp, ldb, kstep, n);
+        }
+        mm('N', 'N', m, n, kstep, -1.0, Yp.p, m, Bp, ldb, 1.0, A, lda);             // A = A - Qp Bp (RRA:1750-1751)
+        copy_matrix(Yp.p, m, Q + c0 * ldq, ldq, m, kstep);                          // Q(:,block) (RRA:1760)
+        frank = (step + 1) * kstep;                                                 // RRA:1770
+        if (tolMode) {                                                              // RRA:1771-1777 (absolute Frobenius norm)
+            sumsq_async(A, lda, m, n, sums.p);
+            allreduce_sum(sums.p, 1);
+            tol_check_kernel<<<1, 1, 0, c.stream>>>(sums.p, tol, done, sums.p + 1);
+            count_launch();
+            RSVD_CUDA(cudaMemcpyAsync(c.h_flag + 24, done, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+            RSVD_CUDA(cudaStreamSynchronize(c.stream));
+            if (c.verbose) {
+                double nv = 0;
+                cudaMemcpy(&nv, sums.p + 1, 8, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[rsvd_b200] randQB step %lld: ||A_res||_F = %g\n", (long long)step, nv);
+            }
+            if (c.h_flag[24]) break;
+        }
+        if (g_status) break;
+    }
+    *frank_out = frank;
+    return g_status;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ID family
+// ---------------------------------------------------------------------------------------------------------
+// shared tail (RRA:1938-1956 / 1836-1850): pivoted QR of Y (r x n, destroyed), I, T = R11^{-1} R12 with k rows
+static void id_tail(double *Y, i64 ldy, i64 r, i64 n, i64 k, double *I, double *T, i64 ldt) {
+    geqp3(Y, ldy, r, n, I);
+    if (n > k) {
+        copy_matrix(Y + k * ldy, ldy, T, ldt, k, n - k);         // Rk2 = R(0:k, k:n)
+        trsm_left_upper(Y, ldy, k, T, ldt, n - k);               // T = triu(Rk1)^{-1} Rk2  (dtrsm reads only the upper triangle)
+    }
+}
+
+int id_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, const double *omega,
+            double *I, double *T, i64 ldt) {
+    ensure_init();
+    Ctx &c = ctx();
+    if (!c.inited) return 1;
+    const i64 l = k + p;
+    if (k <= 0 || p < 0 || s <= 0 || l > n) { set_error("rsvd_b200: invalid parameters k=%lld p=%lld s=%d", (long long)k, (long long)p, s); return 1; }
+    // The reference keeps Y as l x n and transposes around every QR (RRA:1889-1921); here the panels are held
+    // transposed (tall) throughout: Yt = Y^T (n x l), Wt = (Z M^T)^T = M Z^T (m x l).
+    DBuf Yt((size_t)n * l), Wt((size_t)m * l);
+    if (omega) {   // omega is the reference's RN, l x m column-major (global rows; this rank uses columns row0..row0+m)
+        mm('T', 'T', n, l, m, 1.0, A, lda, omega + c.row0 * l, l, 0.0, Yt.p, n);
+    } else {
+        sketch('T', n, l, m, A, lda, seed, l, 1, c.row0 * l, Yt.p, n);              // Y = RN M (RRA:1877), RN(c,i) at i*l + c
+    }
+    allreduce_sum(Yt.p, (size_t)n * l);
+    for (int j = 1; j <= q; ++j) {                                                  // NOTE j <= q (RRA:1882)
+        if ((2 * j - 2) % s == 0) orthonormalize(Yt.p, n, n, l, nullptr, 0, false); // Z = qr(Y')' (RRA:1889-1894)
+        mm('N', 'N', m, l, n, 1.0, A, lda, Yt.p, n, 0.0, Wt.p, m);                  // Y = Z M^T (RRA:1908)
+        if ((2 * j - 1) % s == 0) orthonormalize(Wt.p, m, m, l, nullptr, 0, true);  // RRA:1912-1917
+        mm('T', 'N', n, l, m, 1.0, A, lda, Wt.p, m, 0.0, Yt.p, n);                  // Y = Z M (RRA:1927)
+        allreduce_sum(Yt.p, (size_t)n * l);
+    }
+    Wt.release();
+    DBuf Y((size_t)l * n);
+    transpose(Yt.p, n, Y.p, l, n, l);
+    Yt.release();
+    id_tail(Y.p, l, l, n, k, I, T, ldt);
+    return g_status;
+}
+
+int id_full(const double *M, i64 k, i64 n, i64 ldm, double *I, double *T, i64 ldt) {
+    ensure_init();
+    if (!ctx().inited) return 1;
+    DBuf W((size_t)k * n);
+    copy_matrix(M, ldm, W.p, k, k, n);
+    id_tail(W.p, k, k, n, k, I, T, ldt);
+    return g_status;
+}
+
+int id_two_sided_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed,
+                      double *Icol, double *Irow, double *T, i64 ldt, double *S, i64 lds, i64 m_global) {
+    Ctx &c = ctx();
+    if (id_rand(A, m, n, lda, k, p, q, s, seed, nullptr, Icol, T, ldt)) return 1;  // RRA:2068
+    DBuf MI((size_t)m * k);
+    gather_cols(A, lda, m, Icol, k, MI.p, m);                                        // MI = M(:, Icol(1:k)) (RRA:2073)
+    if (c.world == 1) {
+        DBuf MIt((size_t)k * m);
+        transpose(MI.p, m, MIt.p, k, m, k);                                          // RRA:2074
+        MI.release();
+        id_tail(MIt.p, k, k, m, k, Irow, S, lds);                                    // RRA:2078 -> RRA:1830-1850
+    } else {
+        // row-sharded MI: assemble the full k x m_global transpose on every rank (zero-padded sum), then replicate
+        DBuf MIt((size_t)k * m_global);
+        set_zero(MIt.p, (size_t)k * m_global);
+        transpose(MI.p, m, MIt.p + c.row0 * k, k, m, k);
+        MI.release();
+        allreduce_sum(MIt.p, (size_t)k * m_global);
+        id_tail(MIt.p, k, k, m_global, k, Irow, S, lds);
+    }
+    return g_status;
+}
+
+int cur_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed,
+             double *Cm, i64 ldc, double *U, i64 ldu, double *R, i64 ldr, i64 m_global) {
+    ensure_init();
+    Ctx &c = ctx();
+    if (!c.inited) return 1;
+    DBuf Icol((size_t)n), Irow((size_t)m_global), T((size_t)k * max((i64)1, n - k)), S((size_t)k * max((i64)1, m_global - k));
+    if (id_two_sided_rand(A, m, n, lda, k, p, q, s, seed, Icol.p, Irow.p, T.p, k, S.p, k, m_global)) return 1;   // RRA:2198
+    S.release();
+    DBuf V((size_t)n * k);
+    {
+        i64 total = n * k;
+        int blocks = (int)min((i64)c.sms * 8, (total + 255) / 256);
+        build_v_kernel<<<max(blocks, 1), 256, 0, c.stream>>>(Icol.p, T.p, k, n, k, V.p, n);   // RRA:2200-2219
+        count_launch();
+    }
+    {   // R = M(Irow(1:k), :)  (RRA:2230-2231)
+        i64 total = k * n;
+        int blocks = (int)min((i64)c.sms * 8, (total + 255) / 256);
+        if (c.world == 1) gather_rows(A, lda, n, Irow.p, k, R, ldr);
+        else {
+            DBuf t((size_t)k * n);
+            gather_rows_owned_kernel<<<max(blocks, 1), 256, 0, c.stream>>>(A, lda, m, n, c.row0, Irow.p, k, t.p, k);
+            count_launch();
+            allreduce_sum(t.p, (size_t)k * n);
+            copy_matrix(t.p, k, R, ldr, k, n);
+        }
+    }
+    gather_cols(A, lda, m, Icol.p, k, Cm, ldc);                                      // C = M(:, Icol(1:k)) (RRA:2236-2237)
+    DBuf RRt((size_t)k * k), RV((size_t)k * k), Rt((size_t)n * k);
+    transpose(R, ldr, Rt.p, n, k, n);
+    mm('T', 'N', k, k, n, 1.0, Rt.p, n, Rt.p, n, 0.0, RRt.p, k);                     // R R^T (RRA:2247)
+    mm('T', 'N', k, k, n, 1.0, Rt.p, n, V.p, n, 0.0, RV.p, k);                       // R V   (RRA:2248)
+    int info = lu_solve(RRt.p, k, k, RV.p, k, k);                                    // (R R^T) U^T = R V (RRA:2250)
+    if (info) set_error("rsvd_b200: CUR core solve hit a zero pivot at column %d", info);
+    transpose(RV.p, k, U, ldu, k, k);                                                // U = (U^T)^T (RRA:2252)
+    return g_status;
+}
+
+// streamed 100*||A - U diag(S) V^T||_F / ||A||_F
+double svd_percent_error(const double *A, i64 m, i64 n, i64 lda, const double *U, i64 ldu, const double *S,
+                         const double *V, i64 ldv, i64 k) {
+    ensure_init();
+    Ctx &c = ctx();
+    if (!c.inited) return -1.0;
+    DBuf SVt((size_t)k * n), Vs((size_t)n * k), sums(2);
+    copy_matrix(V, ldv, Vs.p, n, n, k);
+    scale_cols(Vs.p, n, n, k, S, 0);
+    transpose(Vs.p, n, SVt.p, k, n, k);     // (V S)^T = S V^T, k x n
+    Vs.release();
+    i64 nb = max((i64)128, min(n, (i64)((1ull << 30) / (8ull * (size_t)m))));
+    nb = (nb / 128) * 128; if (nb <= 0) nb = 128;
+    DBuf D((size_t)m * min(nb, n));
+    double res2 = 0.0, a2 = 0.0;
+    for (i64 j0 = 0; j0 < n; j0 += nb) {
+        i64 w = min(nb, n - j0);
+        copy_matrix(A + j0 * lda, lda, D.p, m, m, w);
+        double h[2];
+        sumsq_async(D.p, m, m, w, sums.p);
+        mm('N', 'N', m, w, k, -1.0, U, ldu, SVt.p + j0 * k, k, 1.0, D.p, m);
+        sumsq_async(D.p, m, m, w, sums.p + 1);
+        RSVD_CUDA(cudaMemcpyAsync(h, sums.p, 16, cudaMemcpyDeviceToHost, c.stream));
+        RSVD_CUDA(cudaStreamSynchronize(c.stream));
+        a2 += h[0]; res2 += h[1];
+    }
+    if (c.world > 1) {
+        double h[2] = {a2, res2};
+        RSVD_CUDA(cudaMemcpyAsync(sums.p, h, 16, cudaMemcpyHostToDevice, c.stream));
+        allreduce_sum(sums.p, 2);
+        RSVD_CUDA(cudaMemcpyAsync(h, sums.p, 16, cudaMemcpyDeviceToHost, c.stream));
+        RSVD_CUDA(cudaStreamSynchronize(c.stream));
+        a2 = h[0]; res2 = h[1];
+    }
+    return 100.0 * sqrt(res2) / sqrt(a2);
+}
+
+}  // namespace rsvd

@@ -1,0 +1,246 @@
+// runtime.cu — context, out-of-band error channel, stream-ordered device memory, pinned host memory and
+// chunked host<->device staging.  The reference has none of this (its MKL build never leaves the host; its
+// cuBLAS build re-uploads both operands on EVERY GEMM call, matrix_vector_functions_mkl_and_cublas.c:566-577);
+// here one upload per API call keeps A resident for all 2q passes.
+#include "common.cuh"
+#include <stdarg.h>
+#include <mutex>
+
+namespace rsvd {
+
+int g_status = 0;
+static char g_errbuf[1024] = "";
+static std::mutex g_err_mu;
+
+void set_error(const char *fmt, ...) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    if (g_status == 0) {   // keep the first error
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(g_errbuf, sizeof(g_errbuf), fmt, ap);
+        va_end(ap);
+        g_status = 1;
+        if (getenv("RSVD_B200_VERBOSE")) fprintf(stderr, "[rsvd_b200] error: %s\n", g_errbuf);
+    }
+}
+
+Ctx &ctx() {
+    static Ctx c;
+    return c;
+}
+
+static int init_device(int device) {
+    Ctx &c = ctx();
+    if (c.inited) return 0;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        set_error("rsvd_b200: no CUDA device available (%s); there is no CPU fallback", cudaGetErrorString(e));
+        return 1;
+    }
+    if (device < 0) {
+        const char *s = getenv("RSVD_B200_DEVICE");
+        if (!s) s = getenv("LOCAL_RANK");
+        device = s ? atoi(s) : 0;
+        if (device >= ndev) device = device % ndev;
+    }
+    RSVD_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RSVD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("rsvd_b200: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return 1;
+    }
+    c.device = device;
+    c.sms = prop.multiProcessorCount;
+    RSVD_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    RSVD_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    // keep freed blocks in the pool: cudaMallocAsync then costs microseconds, not a driver round trip
+    cudaMemPool_t pool;
+    RSVD_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long thr = ~0ull;
+    RSVD_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    RSVD_CUDA(cudaMalloc(&c.d_flag, 64 * sizeof(int)));
+    RSVD_CUDA(cudaMemset(c.d_flag, 0, 64 * sizeof(int)));
+    RSVD_CUDA(cudaHostAlloc(&c.h_flag, 64 * sizeof(int), cudaHostAllocDefault));
+    const char *v = getenv("RSVD_B200_VERBOSE");
+    c.verbose = v ? atoi(v) : 0;
+    const char *fg = getenv("RSVD_B200_FORCE_GENERIC_GEMM");
+    c.force_generic_gemm = fg ? atoi(fg) : 0;
+    c.inited = (g_status == 0);
+    return g_status;
+}
+
+void ensure_init() {
+    if (!ctx().inited) init_device(-1);
+    else cudaSetDevice(ctx().device);
+}
+
+void *dalloc_bytes(size_t bytes) {
+    ensure_init();
+    if (!ctx().inited) return nullptr;
+    void *p = nullptr;
+    if (bytes == 0) bytes = 8;
+    cudaError_t e = cudaMallocAsync(&p, bytes, ctx().stream);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("rsvd_b200: device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+double *dalloc(size_t n) { return (double *)dalloc_bytes(n * sizeof(double)); }
+void dfree(void *p) {
+    if (p) RSVD_CUDA(cudaFreeAsync(p, ctx().stream));
+}
+
+// ---- host <-> device -------------------------------------------------------------------------------
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+struct Staging {
+    static constexpr size_t CHUNK = 64ull << 20;
+    void *buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    bool ok = false;
+    void init() {
+        if (ok) return;
+        for (int i = 0; i < 2; ++i) {
+            RSVD_CUDA(cudaHostAlloc(&buf[i], CHUNK, cudaHostAllocDefault));
+            RSVD_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        ok = true;
+    }
+};
+static Staging g_staging;
+
+static int copy_h2d(double *d, const double *h, size_t n) {
+    ensure_init();
+    if (!ctx().inited) return 1;
+    size_t bytes = n * 8;
+    cudaStream_t st = ctx().stream;
+    if (bytes == 0) return 0;
+    if (host_is_pinned(h) || bytes < (1u << 20)) {
+        RSVD_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st));
+        RSVD_CUDA(cudaStreamSynchronize(st));
+        return g_status;
+    }
+    // pageable source: double-buffered memcpy -> pinned -> DMA, so the CPU copy of chunk i+1 overlaps the DMA of chunk i
+    g_staging.init();
+    size_t off = 0; int i = 0;
+    bool used[2] = {false, false};
+    while (off < bytes) {
+        size_t c = bytes - off < Staging::CHUNK ? bytes - off : Staging::CHUNK;
+        if (used[i]) RSVD_CUDA(cudaEventSynchronize(g_staging.ev[i]));
+        memcpy(g_staging.buf[i], (const char *)h + off, c);
+        RSVD_CUDA(cudaMemcpyAsync((char *)d + off, g_staging.buf[i], c, cudaMemcpyHostToDevice, st));
+        RSVD_CUDA(cudaEventRecord(g_staging.ev[i], st));
+        used[i] = true;
+        off += c; i ^= 1;
+    }
+    RSVD_CUDA(cudaStreamSynchronize(st));
+    return g_status;
+}
+
+static int copy_d2h(double *h, const double *d, size_t n) {
+    ensure_init();
+    if (!ctx().inited) return 1;
+    size_t bytes = n * 8;
+    cudaStream_t st = ctx().stream;
+    if (bytes == 0) return 0;
+    if (host_is_pinned(h) || bytes < (1u << 20)) {
+        RSVD_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st));
+        RSVD_CUDA(cudaStreamSynchronize(st));
+        return g_status;
+    }
+    g_staging.init();
+    size_t off = 0; int i = 0;
+    size_t pend_off[2] = {0, 0}, pend_c[2] = {0, 0};
+    bool used[2] = {false, false};
+    while (off < bytes || used[0] || used[1]) {
+        if (used[i]) {
+            RSVD_CUDA(cudaEventSynchronize(g_staging.ev[i]));
+            memcpy((char *)h + pend_off[i], g_staging.buf[i], pend_c[i]);
+            used[i] = false;
+        }
+        if (off < bytes) {
+            size_t c = bytes - off < Staging::CHUNK ? bytes - off : Staging::CHUNK;
+            RSVD_CUDA(cudaMemcpyAsync(g_staging.buf[i], (const char *)d + off, c, cudaMemcpyDeviceToHost, st));
+            RSVD_CUDA(cudaEventRecord(g_staging.ev[i], st));
+            pend_off[i] = off; pend_c[i] = c; used[i] = true;
+            off += c;
+        }
+        i ^= 1;
+    }
+    return g_status;
+}
+
+}  // namespace rsvd
+
+using namespace rsvd;
+
+extern "C" {
+
+int rsvd_b200_init(int device) { return init_device(device); }
+int rsvd_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+int rsvd_b200_status(void) { return g_status; }
+const char *rsvd_b200_last_error(void) { return g_errbuf; }
+void rsvd_b200_clear_error(void) { g_status = 0; g_errbuf[0] = 0; }
+void *rsvd_b200_stream(void) { ensure_init(); return (void *)ctx().stream; }
+void rsvd_b200_sync(void) { if (ctx().inited) RSVD_CUDA(cudaStreamSynchronize(ctx().stream)); }
+unsigned long long rsvd_b200_launch_count(void) { return ctx().launches; }
+
+static unsigned long long g_seed_opt = 777ull;
+void rsvd_b200_set_option(const char *name, rsvd_i64 value) {
+    if (!strcmp(name, "seed")) g_seed_opt = (unsigned long long)value;
+    else if (!strcmp(name, "verbose")) ctx().verbose = (int)value;
+    else if (!strcmp(name, "force_generic_gemm")) ctx().force_generic_gemm = (int)value;
+    else if (!strcmp(name, "force_qr_fallback")) ctx().force_qr_fallback = (int)value;
+    else if (!strcmp(name, "row0")) ctx().row0 = value;
+    else if (!strcmp(name, "m_global")) ctx().m_global = value;
+    else set_error("rsvd_b200_set_option: unknown option '%s'", name);
+}
+rsvd_i64 rsvd_b200_get_option(const char *name) {
+    if (!strcmp(name, "seed")) return (rsvd_i64)g_seed_opt;
+    if (!strcmp(name, "verbose")) return ctx().verbose;
+    if (!strcmp(name, "force_generic_gemm")) return ctx().force_generic_gemm;
+    if (!strcmp(name, "force_qr_fallback")) return ctx().force_qr_fallback;
+    if (!strcmp(name, "last_gemm_path")) return g_last_gemm_path;
+    if (!strcmp(name, "last_qr_path")) return ctx().last_qr_path;
+    if (!strcmp(name, "qr_fallbacks")) return (rsvd_i64)ctx().qr_fallbacks;
+    if (!strcmp(name, "sms")) { ensure_init(); return ctx().sms; }
+    if (!strcmp(name, "rank")) return ctx().rank;
+    if (!strcmp(name, "row0")) return ctx().row0;
+    if (!strcmp(name, "m_global")) return ctx().m_global;
+    if (!strcmp(name, "world")) return ctx().world;
+    return -1;
+}
+
+double *rsvd_b200_dev_alloc(rsvd_i64 n) { return dalloc((size_t)n); }
+void rsvd_b200_dev_free(double *d) { dfree(d); }
+int rsvd_b200_h2d(double *d, const double *h, rsvd_i64 n) { return copy_h2d(d, h, (size_t)n); }
+int rsvd_b200_d2h(double *h, const double *d, rsvd_i64 n) { return copy_d2h(h, d, (size_t)n); }
+
+void *rsvd_b200_host_alloc(size_t bytes) {
+    ensure_init();
+    if (!ctx().inited) return nullptr;
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 8, cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    memset(p, 0, bytes);
+    return p;
+}
+void rsvd_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

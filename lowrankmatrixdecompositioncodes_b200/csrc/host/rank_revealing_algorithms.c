@@ -1,0 +1,369 @@
+/* rank_revealing_algorithms.c — C host side of the algorithms layer (reference: rank_revealing_algorithms_intel_mkl.c
+ * = RRA).  Each exported function keeps the reference's name, argument order, output allocation rules
+ * (callee allocates with matrix_new/vector_new, caller frees) and parameter quirks, uploads M once, runs the whole
+ * algorithm on the B200 through the C-ABI of rsvd_b200.h, and downloads the factors.  The host never touches the
+ * numbers in between: A stays resident in HBM for all passes. */
+#include "rank_revealing_algorithms_intel_mkl.h"
+#include "rsvd_b200.h"
+#include "rsvd_b200_host_util.h"
+#include <stdarg.h>
+
+typedef RSVD_INT idx_t;
+
+/* ---- status ------------------------------------------------------------------------------------------------------ */
+static int g_api_status = 0;
+static char g_api_err[1024] = "";
+static double g_last_percent_error = -1.0;
+
+void rsvd_api_error(const char *fmt, ...) {
+    if (g_api_status) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_api_err, sizeof(g_api_err), fmt, ap);
+    va_end(ap);
+    g_api_status = 1;
+    if (getenv("RSVD_B200_VERBOSE")) fprintf(stderr, "[rsvd_b200 api] %s\n", g_api_err);
+}
+void rsvd_api_sync_error(void) {
+    if (rsvd_b200_status()) rsvd_api_error("%s", rsvd_b200_last_error());
+}
+void rsvd_api_begin(void) {
+    g_api_status = 0; g_api_err[0] = 0;
+    rsvd_b200_clear_error();
+}
+int rsvd_b200_api_status(void) { rsvd_api_sync_error(); return g_api_status; }
+const char *rsvd_b200_api_last_error(void) { return g_api_err; }
+double rsvd_b200_api_last_percent_error(void) { return g_last_percent_error; }
+
+static int verbose(void) {
+    static int v = -1;
+    if (v < 0) { const char *s = getenv("RSVD_B200_VERBOSE"); v = s ? atoi(s) : 0; }
+    return v;
+}
+static uint64_t omega_seed(void) { return (uint64_t)rsvd_b200_get_option("seed"); }
+
+static mat *download_mat(const double *d, idx_t r, idx_t c) {
+    mat *M = matrix_new(r, c);
+    rsvd_download(M->d, d, (size_t)r * (size_t)c);
+    return M;
+}
+static vec *download_vec(const double *d, idx_t n) {
+    vec *v = vector_new(n);
+    rsvd_download(v->d, d, (size_t)n);
+    return v;
+}
+static mat *diag_from_device(const double *ds, idx_t k) {
+    mat *S = matrix_new(k, k);
+    double *s = (double *)malloc((size_t)(k ? k : 1) * sizeof(double));
+    rsvd_download(s, ds, (size_t)k);
+    for (idx_t i = 0; i < k; ++i) S->d[(size_t)i * (size_t)k + (size_t)i] = s[i];
+    free(s);
+    return S;
+}
+
+/* ---- low_rank_svd_rand_decomp_fixed_rank (RRA:73-234) -------------------------------------------------------------
+ * *frank is never written by the reference; neither here. */
+void low_rank_svd_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t vnum, idx_t q, idx_t s, idx_t *frank,
+                                         mat **U, mat **S, mat **V) {
+    (void)frank;
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols;
+    *U = NULL; *S = NULL; *V = NULL;
+    if (k <= 0 || p < 0 || s <= 0 || k + p > min(m, n)) {
+        rsvd_api_error("low_rank_svd_rand_decomp_fixed_rank: need 0 < k+p <= min(m,n) and s > 0 (k=%lld p=%lld s=%lld, M %lld x %lld)",
+                       (long long)k, (long long)p, (long long)s, (long long)m, (long long)n);
+        *U = matrix_new(m, max(k, 0)); *S = matrix_new(max(k, 0), max(k, 0)); *V = matrix_new(n, max(k, 0));
+        return;
+    }
+    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dU = rsvd_b200_dev_alloc((rsvd_i64)m * k), *dS = rsvd_b200_dev_alloc(k), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * k);
+    if (dA && dU && dS && dV)
+        rsvd_b200_svd_rand_dev(dA, m, n, m, k, p, (int)vnum, (int)q, (int)s, omega_seed(), NULL, dU, m, dS, dV, n);
+    rsvd_b200_dev_free(dA);
+    *U = download_mat(dU, m, k);
+    *S = diag_from_device(dS, k);
+    *V = download_mat(dV, n, k);
+    rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dS); rsvd_b200_dev_free(dV);
+    rsvd_api_sync_error();
+}
+
+/* ---- randQB_pb_new (RRA:1576-1801) -------------------------------------------------------------------------------- */
+static int randqb_device(mat *M, idx_t kstep, idx_t nstep, double TOL, idx_t q, idx_t s, idx_t *frank,
+                         double **dA_out, double **dQ_out, double **dB_out, idx_t *cap_out) {
+    idx_t m = M->nrows, n = M->ncols, r = min(m, n);
+    if (kstep > (idx_t)(r / 2)) {                       /* RRA:1589-1592 */
+        kstep = (idx_t)r / 10;
+        if (verbose()) printf("kstep resized to %lld\n", (long long)kstep);
+    }
+    if (kstep <= 0 || s <= 0) { rsvd_api_error("randQB_pb_new: invalid kstep/s"); return 1; }
+    idx_t cap;
+    if (nstep <= 0) cap = (idx_t)(r / kstep) * kstep;   /* tolerance mode (RRA:1595-1602) */
+    else cap = kstep * nstep;
+    if (cap > r) cap = (r / kstep) * kstep;
+    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);   /* the private copy A = M (RRA:1630) lives only in HBM */
+    double *dQ = rsvd_b200_dev_alloc((rsvd_i64)m * cap + 1), *dB = rsvd_b200_dev_alloc((rsvd_i64)cap * n + 1);
+    rsvd_i64 fr = 0;
+    if (dA && dQ && dB)
+        rsvd_b200_randqb_dev(dA, m, n, m, kstep, nstep <= 0 ? 0 : cap / kstep, TOL, (int)q, (int)s, omega_seed(), dQ, m, dB, cap, &fr);
+    *frank = (idx_t)fr;
+    *dA_out = dA; *dQ_out = dQ; *dB_out = dB; *cap_out = cap;
+    rsvd_api_sync_error();
+    return g_api_status;
+}
+
+void randQB_pb_new(mat *M, idx_t kstep, idx_t nstep, double TOL, idx_t q, idx_t s, idx_t *frank, mat **Q, mat **B) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols, cap = 0;
+    double *dA = NULL, *dQ = NULL, *dB = NULL;
+    *Q = NULL; *B = NULL;
+    randqb_device(M, kstep, nstep, TOL, q, s, frank, &dA, &dQ, &dB, &cap);
+    rsvd_b200_dev_free(dA);
+    /* rank mode returns all kstep*nstep columns; tolerance mode is cut to frank (RRA:1782-1789) */
+    idx_t cols = (nstep <= 0) ? *frank : cap;
+    if (dQ && dB) {
+        *Q = download_mat(dQ, m, cols);
+        mat *Bfull = download_mat(dB, cap, n);
+        if (cols != cap) resize_matrix_by_rows(&Bfull, cols);
+        *B = Bfull;
+    } else {
+        *Q = matrix_new(m, 0); *B = matrix_new(0, n);
+    }
+    rsvd_b200_dev_free(dQ); rsvd_b200_dev_free(dB);
+    rsvd_api_sync_error();
+}
+
+/* ---- low_rank_svd_blockrand_decomp_fixed_rank_or_prec (RRA:239-381) -------------------------------------------------
+ * Parameter handling follows the reference exactly, including quirk Q1: nstep = (k+p)/kstep by
+ * INTEGER division is computed after the k<=0 branch, so tolerance mode is never reached through this entry point;
+ * call randQB_pb_new(nstep <= 0) for a tolerance-driven QB. */
+void low_rank_svd_blockrand_decomp_fixed_rank_or_prec(mat *M, idx_t k, idx_t p, double TOL, idx_t vnum, idx_t kstep,
+                                                      idx_t q, idx_t s, idx_t *frank, mat **U, mat **S, mat **V) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols;
+    int rankMode = k > 0;
+    if (p < kstep && (p + kstep) < min(m, n)) p = kstep;          /* RRA:260-262 */
+    idx_t nstep = (kstep > 0) ? (k + p) / kstep : 0;              /* RRA:263 */
+    *U = NULL; *S = NULL; *V = NULL;
+    if (nstep <= 0) { rsvd_api_error("low_rank_svd_blockrand: (k+p)/kstep = 0 blocks"); *U = matrix_new(m, 0); *S = matrix_new(0, 0); *V = matrix_new(n, 0); return; }
+    idx_t cap = 0, fr = 0;
+    double *dA = NULL, *dQ = NULL, *dB = NULL;
+    if (randqb_device(M, kstep, nstep, TOL, q, s, &fr, &dA, &dQ, &dB, &cap)) {
+        rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dQ); rsvd_b200_dev_free(dB);
+        *U = matrix_new(m, 0); *S = matrix_new(0, 0); *V = matrix_new(n, 0);
+        return;
+    }
+    rsvd_b200_dev_free(dB);                                        /* the SVD tail recomputes from M and Q (RRA:289-380) */
+    idx_t l = cap;                                                 /* l = B->nrows (RRA:271) */
+    if (rankMode) *frank = k;                                      /* RRA:274-275 */
+    else *frank = (idx_t)round(((double)fr / ((double)fr + (double)p + 1e-6)) * (double)fr);   /* RRA:278 */
+    idx_t kk = *frank;
+    if (kk > l) kk = l;
+    /* the residual in dA is replaced by the original M for the tail */
+    if (rsvd_b200_h2d(dA, M->d, (rsvd_i64)m * n)) rsvd_api_sync_error();
+    double *dU = rsvd_b200_dev_alloc((rsvd_i64)m * kk + 1), *dS = rsvd_b200_dev_alloc(kk + 1), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * kk + 1);
+    if (dU && dS && dV) rsvd_b200_svd_from_q_dev(dA, m, n, m, dQ, m, l, kk, (int)vnum, dU, m, dS, dV, n);
+    rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dQ);
+    *U = download_mat(dU, m, kk);
+    *S = diag_from_device(dS, kk);
+    *V = download_mat(dV, n, kk);
+    rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dS); rsvd_b200_dev_free(dV);
+    rsvd_api_sync_error();
+}
+
+/* ---- pivotedQR_mkl (RRA:924-976) ------------------------------------------------------------------------------------
+ * R and I come from the dgeqp3-compatible device kernel.  The reference also returns the explicit Q (never read on the
+ * hot path); it is rebuilt here as M(:,I(1:k)) * R11^{-1}, which equals the Householder Q when R11 is nonsingular. */
+void pivotedQR_mkl(mat *M, mat **Q, mat **R, vec **I) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols, k = min(m, n);
+    idx_t Rcols = (m <= n) ? n : k;
+    double *dW = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dI = rsvd_b200_dev_alloc(n + 1);
+    *Q = NULL; *R = NULL; *I = NULL;
+    if (dW && dI) rsvd_b200_geqp3(dW, m, m, n, dI);
+    mat *W = download_mat(dW, m, n);
+    *I = download_vec(dI, n);
+    rsvd_b200_dev_free(dW); rsvd_b200_dev_free(dI);
+    *R = matrix_new(k, Rcols);
+    for (idx_t j = 0; j < Rcols; ++j)
+        for (idx_t i = 0; i <= j && i < k; ++i) (*R)->d[(size_t)j * k + i] = W->d[(size_t)j * m + i];
+    matrix_delete(W);
+    /* Q = M(:, I(1:k)) R11^{-1}  <=>  Q^T = R11^{-T} M(:,I)^T : solve with the transposed system via R11^T Q^T = MI^T */
+    mat *MI = matrix_new(m, k);
+    fill_matrix_from_first_columns_from_list(M, *I, k, MI);
+    mat *R11 = matrix_new(k, k), *R11inv = matrix_new(k, k), *Ik = matrix_new(k, k);
+    fill_matrix_from_first_columns(*R, k, R11);
+    initialize_identity_matrix(Ik);
+    upper_triangular_system_solve(R11, Ik, R11inv, 1);
+    *Q = matrix_new(m, k);
+    matrix_matrix_mult(MI, R11inv, *Q);
+    matrix_delete(MI); matrix_delete(R11); matrix_delete(R11inv); matrix_delete(Ik);
+    rsvd_api_sync_error();
+}
+
+/* ---- ID family ---------------------------------------------------------------------------------------------------- */
+void id_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t q, idx_t s, vec **I, mat **T) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols;
+    *I = NULL; *T = NULL;
+    if (k <= 0 || p < 0 || s <= 0 || k + p > min(m, n)) {
+        rsvd_api_error("id_rand_decomp_fixed_rank: need 0 < k+p <= min(m,n) and s > 0");
+        *I = vector_new(n); *T = matrix_new(max(k, 0), n - max(k, 0));
+        return;
+    }
+    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dI = rsvd_b200_dev_alloc(n + 1), *dT = rsvd_b200_dev_alloc((rsvd_i64)k * (n - k) + 1);
+    if (dA && dI && dT) rsvd_b200_id_rand_dev(dA, m, n, m, k, p, (int)q, (int)s, omega_seed(), NULL, dI, dT, k);
+    rsvd_b200_dev_free(dA);
+    *I = download_vec(dI, n);
+    *T = download_mat(dT, k, n - k);
+    rsvd_b200_dev_free(dI); rsvd_b200_dev_free(dT);
+    rsvd_api_sync_error();
+}
+
+/* RRA:1807-1854.  Only the branch the hot path reaches (k == min(m,n): full dgeqp3, RRA:1830-1834) is on the device;
+ * the partial-rank Householder branch (RRA:1828-1829) is a deterministic baseline outside the north-star path. */
+void id_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, vec **I, mat **T) {
+    (void)TOL;
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols;
+    *I = NULL; *T = NULL;
+    if (k < min(m, n) || k <= 0) {
+        rsvd_api_error("id_decomp_fixed_rank_or_prec: only k == min(m,n) (full pivoted QR) is implemented (k=%lld, M %lld x %lld)",
+                       (long long)k, (long long)m, (long long)n);
+        *I = vector_new(n); *T = matrix_new(max(k, 0), max(n - k, 0));
+        return;
+    }
+    if (m > n) { rsvd_api_error("id_decomp_fixed_rank_or_prec: need nrows <= ncols"); *I = vector_new(n); *T = matrix_new(k, 0); return; }
+    *frank = k;
+    double *dM = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dI = rsvd_b200_dev_alloc(n + 1), *dT = rsvd_b200_dev_alloc((rsvd_i64)k * (n - k) + 1);
+    if (dM && dI && dT) rsvd_b200_id_full_dev(dM, k, n, m, dI, dT, k);
+    rsvd_b200_dev_free(dM);
+    *I = download_vec(dI, n);
+    *T = download_mat(dT, k, n - k);
+    rsvd_b200_dev_free(dI); rsvd_b200_dev_free(dT);
+    rsvd_api_sync_error();
+}
+
+void id_two_sided_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t q, idx_t s, vec **Icol, vec **Irow, mat **T, mat **S) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols;
+    *Icol = NULL; *Irow = NULL; *T = NULL; *S = NULL;
+    if (k <= 0 || p < 0 || s <= 0 || k + p > min(m, n)) {
+        rsvd_api_error("id_two_sided_rand_decomp_fixed_rank: need 0 < k+p <= min(m,n) and s > 0");
+        *Icol = vector_new(n); *Irow = vector_new(m); *T = matrix_new(max(k, 0), n - max(k, 0)); *S = matrix_new(max(k, 0), m - max(k, 0));
+        return;
+    }
+    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dIc = rsvd_b200_dev_alloc(n + 1), *dIr = rsvd_b200_dev_alloc(m + 1);
+    double *dT = rsvd_b200_dev_alloc((rsvd_i64)k * (n - k) + 1), *dS = rsvd_b200_dev_alloc((rsvd_i64)k * (m - k) + 1);
+    if (dA && dIc && dIr && dT && dS)
+        rsvd_b200_id_two_sided_rand_dev(dA, m, n, m, k, p, (int)q, (int)s, omega_seed(), dIc, dIr, dT, k, dS, k);
+    rsvd_b200_dev_free(dA);
+    *Icol = download_vec(dIc, n); *Irow = download_vec(dIr, m);
+    *T = download_mat(dT, k, n - k); *S = download_mat(dS, k, m - k);
+    rsvd_b200_dev_free(dIc); rsvd_b200_dev_free(dIr); rsvd_b200_dev_free(dT); rsvd_b200_dev_free(dS);
+    rsvd_api_sync_error();
+}
+
+void cur_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t q, idx_t s, mat **C, mat **U, mat **R) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols;
+    *C = NULL; *U = NULL; *R = NULL;
+    if (k <= 0 || p < 0 || s <= 0 || k + p > min(m, n)) {
+        rsvd_api_error("cur_rand_decomp_fixed_rank: need 0 < k+p <= min(m,n) and s > 0");
+        *C = matrix_new(m, max(k, 0)); *U = matrix_new(max(k, 0), max(k, 0)); *R = matrix_new(max(k, 0), n);
+        return;
+    }
+    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dC = rsvd_b200_dev_alloc((rsvd_i64)m * k + 1), *dU = rsvd_b200_dev_alloc((rsvd_i64)k * k + 1), *dR = rsvd_b200_dev_alloc((rsvd_i64)k * n + 1);
+    if (dA && dC && dU && dR)
+        rsvd_b200_cur_rand_dev(dA, m, n, m, k, p, (int)q, (int)s, omega_seed(), dC, m, dU, k, dR, k);
+    rsvd_b200_dev_free(dA);
+    *C = download_mat(dC, m, k); *U = download_mat(dU, k, k); *R = download_mat(dR, k, n);
+    rsvd_b200_dev_free(dC); rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dR);
+    rsvd_api_sync_error();
+}
+
+/* ---- evaluation helpers (RRA:2337-2573): 100*||M - approx||_F/||M||_F, printed like the reference ------------------- */
+void use_low_rank_svd_for_approximation(mat *M, mat *U, mat *S, mat *V) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols, k = S->nrows;
+    double *s = (double *)malloc((size_t)(k ? k : 1) * sizeof(double));
+    for (idx_t i = 0; i < k; ++i) s[i] = S->d[(size_t)i * k + i];
+    double *dA = rsvd_upload(M->d, (size_t)m * n), *dU = rsvd_upload(U->d, (size_t)m * k), *dV = rsvd_upload(V->d, (size_t)n * k),
+           *dS = rsvd_upload(s, (size_t)k);
+    free(s);
+    double pe = -1.0;
+    if (dA && dU && dV && dS) pe = rsvd_b200_svd_percent_error_dev(dA, m, n, m, dU, m, dS, dV, n, k);   /* streamed, no dense m x n product */
+    rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dV); rsvd_b200_dev_free(dS);
+    g_last_percent_error = pe;
+    printf("percent_error between M and U S V^T = %f\n", pe);
+    rsvd_api_sync_error();
+}
+
+static void report(mat *M, mat *P, const char *what) {
+    g_last_percent_error = get_percent_error_between_two_mats(M, P);
+    printf("percent_error between M and %s = %f\n", what, g_last_percent_error);
+}
+
+void use_QB_decomp_for_approximation(mat *M, mat *Q, mat *B) {
+    rsvd_api_begin();
+    mat *P = matrix_new(M->nrows, M->ncols);
+    matrix_matrix_mult(Q, B, P);
+    report(M, P, "QB");
+    matrix_delete(P);
+}
+
+/* M ~ M(:,I(1:k)) [I_k T] P^T  (RRA:2402-2476) */
+void use_id_decomp_for_approximation(mat *M, mat *T, vec *I, idx_t k) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols;
+    mat *C = matrix_new(m, k), *CT = matrix_new(m, n - k), *P = matrix_new(m, n);
+    fill_matrix_from_first_columns_from_list(M, I, k, C);
+    matrix_matrix_mult(C, T, CT);
+    for (idx_t j = 0; j < n; ++j) {
+        idx_t dst = (idx_t)I->d[j];
+        const double *src = (j < k) ? &C->d[(size_t)j * m] : &CT->d[(size_t)(j - k) * m];
+        memcpy(&P->d[(size_t)dst * m], src, (size_t)m * sizeof(double));
+    }
+    report(M, P, "ID approximation");
+    matrix_delete(C); matrix_delete(CT); matrix_delete(P);
+}
+
+/* M ~ [I_k S]^T(Irow^{-1}) M(Irow(1:k), Icol(1:k)) [I_k T](Icol^{-1})  (RRA:2481-2558) */
+void use_id_two_sided_decomp_for_approximation(mat *M, mat *T, mat *S, vec *Icol, vec *Irow, idx_t k) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols;
+    mat *Ms = matrix_new(k, k);
+    for (idx_t j = 0; j < k; ++j)
+        for (idx_t i = 0; i < k; ++i)
+            Ms->d[(size_t)j * k + i] = M->d[(size_t)((idx_t)Icol->d[j]) * m + (idx_t)Irow->d[i]];
+    /* W = Ms [I T] with columns scattered by Icol (k x n) */
+    mat *MsT = matrix_new(k, n - k), *W = matrix_new(k, n);
+    matrix_matrix_mult(Ms, T, MsT);
+    for (idx_t j = 0; j < n; ++j) {
+        idx_t dst = (idx_t)Icol->d[j];
+        const double *src = (j < k) ? &Ms->d[(size_t)j * k] : &MsT->d[(size_t)(j - k) * k];
+        memcpy(&W->d[(size_t)dst * k], src, (size_t)k * sizeof(double));
+    }
+    /* P = [I S]^T W with rows scattered by Irow (m x n) */
+    mat *StW = matrix_new(m - k, n), *P = matrix_new(m, n);
+    matrix_transpose_matrix_mult(S, W, StW);
+    for (idx_t j = 0; j < n; ++j)
+        for (idx_t i = 0; i < m; ++i) {
+            idx_t dst = (idx_t)Irow->d[i];
+            P->d[(size_t)j * m + dst] = (i < k) ? W->d[(size_t)j * k + i] : StW->d[(size_t)j * (m - k) + (i - k)];
+        }
+    report(M, P, "two sided ID approximation");
+    matrix_delete(Ms); matrix_delete(MsT); matrix_delete(W); matrix_delete(StW); matrix_delete(P);
+}
+
+void use_cur_decomp_for_approximation(mat *M, mat *C, mat *U, mat *R) {
+    rsvd_api_begin();
+    mat *P = matrix_new(M->nrows, M->ncols);
+    form_cur_product_matrix(C, U, R, P);
+    report(M, P, "C U R");
+    matrix_delete(P);
+}
