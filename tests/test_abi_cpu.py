@@ -1,0 +1,132 @@
+"""CPU tests of the boundary: the three shared libraries load without a GPU, export every symbol the headers
+declare, keep the reference's struct layout, fail loudly (no CPU fallback), and the host-only pieces (allocation,
+slicing helpers, both binary file formats, row partition) behave like the reference's."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import lowrankmatrixdecompositioncodes_b200 as pkg
+from lowrankmatrixdecompositioncodes_b200 import native
+from oracle import rsvd_numpy as O
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", " ".join(
+        l for l in txt.splitlines() if not l.strip().startswith("#")))) - {"defined", "sizeof"})
+
+
+def test_device_layer_exports_every_declared_symbol():
+    lib = native.dev()
+    names = [n for n in _declared("rsvd_b200.h") if n.startswith("rsvd_b200_")]
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(native.SIGNATURES) == names   # the ctypes table covers the whole header
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_api_libraries_export_reference_symbols(bits):
+    api = pkg.Api(bits)
+    names = [n for n in _declared("rsvd_b200_rra_decl.h") + _declared("rsvd_b200_matvec_decl.h")
+             if n not in ("min", "max", "x", "y")]
+    assert "low_rank_svd_rand_decomp_fixed_rank" in names and "matrix_load_from_binary_file" in names
+    for n in names:
+        assert hasattr(api.lib, n), n
+
+
+def test_struct_layout_matches_reference():
+    a32, a64 = pkg.Api(32), pkg.Api(64)
+    assert C.sizeof(a32.Mat) == 16 and C.sizeof(a32.Vec) == 16    # {int,int,double*}, {int,double*}  (MVH:18-27)
+    assert C.sizeof(a64.Mat) == 24 and C.sizeof(a64.Vec) == 16    # int64_t twins
+    assert a32.Mat.d.offset == 8 and a64.Mat.d.offset == 16
+
+
+def test_no_cpu_fallback_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    api = pkg.Api(32)
+    with pytest.raises(RuntimeError, match="no CUDA device|CPU fallback"):
+        api.svd_rand(np.random.rand(30, 20), 4, 2)
+    with pytest.raises(RuntimeError):
+        api.id_rand(np.random.rand(30, 20), 4, 2, 1, 1)
+    native.dev().rsvd_b200_clear_error()
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_binary_io_both_formats(bits, tmp_path):
+    api = pkg.Api(bits)
+    A = np.random.default_rng(0).standard_normal((37, 91))
+    f = str(tmp_path / "a.bin")
+    O.write_matrix_binary(A, f, bits)                       # the reference's format (make_matrix_binary.m:32-41)
+    M = api.lib.matrix_load_from_binary_file(f.encode())
+    assert np.array_equal(api.from_mat(M), A)
+    g = str(tmp_path / "b.bin")
+    M = api.to_mat(A)
+    api.lib.matrix_write_to_binary_file(M, g.encode())
+    api.lib.matrix_delete(M)
+    assert open(f, "rb").read() == open(g, "rb").read()
+    assert os.path.getsize(g) == (8 if bits == 32 else 16) + 37 * 91 * 8
+    # ragged / empty
+    E = np.zeros((0, 5))
+    O.write_matrix_binary(E, f, bits)
+    M = api.lib.matrix_load_from_binary_file(f.encode())
+    assert api.from_mat(M).shape == (0, 5)
+
+
+def test_io_file_interchange_with_reference(ref32, tmp_path):
+    api = pkg.Api(32)
+    A = np.random.default_rng(1).standard_normal((13, 7))
+    f = str(tmp_path / "x.bin")
+    M = api.to_mat(A)
+    api.lib.matrix_write_to_binary_file(M, f.encode())
+    api.lib.matrix_delete(M)
+    R = ref32.lib.matrix_load_from_binary_file(f.encode())
+    assert np.array_equal(ref32.from_mat(R), A)
+
+
+def test_host_slicing_helpers_match_reference(ref32):
+    api = pkg.Api(32)
+    A = np.random.default_rng(2).standard_normal((9, 6))
+    for name in ["resize_matrix_by_columns", "resize_matrix_by_columns_from_end", "resize_matrix_by_rows",
+                 "resize_matrix_by_rows_from_end"]:
+        for lib_ in (api, ref32):
+            getattr(lib_.lib, name).argtypes = [C.POINTER(C.POINTER(lib_.Mat)), lib_.I]
+        M1, M2 = api.to_mat(A), ref32.to_mat(A)
+        getattr(api.lib, name)(C.byref(M1), 4)
+        getattr(ref32.lib, name)(C.byref(M2), 4)
+        assert np.array_equal(api.from_mat(M1), ref32.from_mat(M2)), name
+    # vector_build_rewrapped + fill_matrix_from_first_rows_from_list (CUR tail helpers, MVF:1195-1201,1029-1042)
+    perm = np.random.default_rng(3).permutation(9).astype(np.float64)
+    outs = []
+    for lib_ in (api, ref32):
+        lib_.lib.vector_build_rewrapped.argtypes = [C.POINTER(lib_.Vec), C.POINTER(lib_.Vec)]
+        lib_.lib.fill_matrix_from_first_rows_from_list.argtypes = [C.POINTER(lib_.Mat), C.POINTER(lib_.Vec), lib_.I, C.POINTER(lib_.Mat)]
+        v = lib_.lib.vector_new(9)
+        np.ctypeslib.as_array(v.contents.d, shape=(9,))[:] = perm
+        vi = lib_.lib.vector_new(9)
+        lib_.lib.vector_build_rewrapped(vi, v)
+        M, Mk = lib_.to_mat(A), lib_.lib.matrix_new(5, 6)
+        lib_.lib.fill_matrix_from_first_rows_from_list(M, v, 5, Mk)
+        outs.append((lib_.from_vec(vi), lib_.from_mat(Mk)))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert api.lib.get_matrix_frobenius_norm(api.to_mat(A)) == pytest.approx(np.linalg.norm(A), rel=1e-14)
+
+
+def test_row_partition_covers_all_rows():
+    for m, w in [(50000, 8), (1000000, 8), (17, 4), (400000, 3), (5, 8)]:
+        tot, prev_end = 0, 0
+        for r in range(w):
+            r0, rows = native.row_partition(m, w, r)
+            assert r0 == min(prev_end, m) and rows >= 0
+            assert r0 % 16 == 0 or rows == 0
+            prev_end = r0 + rows
+            tot += rows
+        assert tot == m

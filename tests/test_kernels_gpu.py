@@ -1,0 +1,215 @@
+"""GPU tests of the individual kernel families through the device-layer C-ABI (device pointers), against torch FP64
+(cuBLAS/cuSOLVER are used ONLY here, as the checker) and scipy LAPACK.  Also size-independent properties at a size
+the oracle cannot run in seconds."""
+import numpy as np
+import pytest
+import torch
+
+from lowrankmatrixdecompositioncodes_b200 import device as D, native
+from oracle import ref_lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    l = native.dev()
+    assert l.rsvd_b200_init(0) == 0, l.rsvd_b200_last_error().decode()
+    return l
+
+
+def sync(lib):
+    lib.rsvd_b200_sync()
+    torch.cuda.synchronize()
+
+
+def run_gemm(lib, ta, tb, m, n, k, alpha, beta, pad, force_generic):
+    g = torch.Generator(device="cpu").manual_seed(m * 7 + n * 3 + k)
+    ar, ac = (m, k) if ta == "N" else (k, m)
+    br, bc = (k, n) if tb == "N" else (n, k)
+    lda, ldb, ldc = ar + pad, br + pad, m + pad
+    A = torch.randn((ac, lda), dtype=torch.float64, generator=g).cuda()
+    B = torch.randn((bc, ldb), dtype=torch.float64, generator=g).cuda()
+    Cm = torch.randn((n, ldc), dtype=torch.float64, generator=g).cuda()
+    C0 = Cm.clone()
+    lib.rsvd_b200_set_option(b"force_generic_gemm", int(force_generic))
+    D.gemm(ta, tb, m, n, k, A, lda, B, ldb, Cm, ldc, alpha, beta)
+    sync(lib)
+    path = lib.rsvd_b200_get_option(b"last_gemm_path")
+    lib.rsvd_b200_set_option(b"force_generic_gemm", 0)
+    opA = A[:, :ar].t() if ta == "N" else A[:, :ar]
+    opB = B[:, :br].t() if tb == "N" else B[:, :br]
+    ref = alpha * (opA @ opB) + beta * C0[:, :m].t()
+    err = ((Cm[:, :m].t() - ref).abs().max() / ref.abs().max()).item()
+    assert torch.equal(Cm[:, m:], C0[:, m:])   # padding rows untouched
+    return err, path
+
+
+@pytest.mark.parametrize("ta,tb,m,n,k", [("N", "N", 100, 70, 50), ("T", "N", 129, 65, 1000), ("N", "T", 64, 64, 16),
+                                         ("T", "T", 33, 17, 9), ("T", "N", 120, 120, 5000), ("N", "N", 1, 1, 1)])
+def test_generic_gemm(lib, ta, tb, m, n, k):
+    err, path = run_gemm(lib, ta, tb, m, n, k, 1.3, 0.7, pad=1, force_generic=True)
+    assert path == 0 and err < 1e-13
+
+
+@pytest.mark.parametrize("ta,m,n,k,alpha,beta", [("N", 1024, 256, 512, 1.0, 0.0), ("T", 1024, 256, 512, 1.0, 0.0),
+                                                 ("N", 1000, 130, 530, 1.5, 0.5), ("T", 778, 120, 2050, -1.0, 1.0),
+                                                 ("T", 520, 520, 50000, 1.0, 0.0), ("N", 5000, 200, 200, -1.0, 1.0),
+                                                 ("N", 4112, 520, 3000, 1.0, 0.0), ("N", 2050, 8, 700, 1.0, 0.0),
+                                                 ("T", 300, 1050, 4000, 1.0, 0.0)])
+def test_tma_gemm(lib, ta, m, n, k, alpha, beta):
+    err, path = run_gemm(lib, ta, "N", m, n, k, alpha, beta, pad=0, force_generic=False)
+    assert err < 2e-13
+    if n >= 16:
+        assert path == 1   # the TMA kernel served it (no silent fallback to the generic kernel)
+
+
+@pytest.mark.parametrize("ta,m,n,k,sk,sc,off", [("N", 2000, 120, 1500, 1, 1500, 0), ("T", 1500, 120, 2000, 120, 1, 240),
+                                                ("N", 4096, 520, 2051, 1, 2051, 5), ("N", 3000, 200, 1000, 1, 1000, 200 * 1000 * 3)])
+def test_fused_philox_sketch_equals_explicit_omega(lib, ta, m, n, k, sk, sc, off):
+    g = torch.Generator(device="cpu").manual_seed(1)
+    ar, ac = (m, k) if ta == "N" else (k, m)
+    A = torch.randn((ac, ar), dtype=torch.float64, generator=g).cuda()
+    idx = off + np.arange(k)[:, None] * sk + np.arange(n)[None, :] * sc
+    flat = ref_lib.normal_stream(99, 0, int(idx.max()) + 1)
+    Om = torch.from_numpy(flat[idx]).cuda()
+    ref = (A.t() if ta == "N" else A) @ Om
+    for force in (0, 1):
+        Cm = torch.empty((n, m), dtype=torch.float64, device="cuda")
+        lib.rsvd_b200_set_option(b"force_generic_gemm", force)
+        native.check(lib.rsvd_b200_sketch(ta.encode(), m, n, k, A.data_ptr(), ar, 99, sk, sc, off, Cm.data_ptr(), m))
+        sync(lib)
+        assert lib.rsvd_b200_get_option(b"last_gemm_path") == 1 - force
+        lib.rsvd_b200_set_option(b"force_generic_gemm", 0)
+        assert ((Cm.t() - ref).abs().max() / ref.abs().max()).item() < 1e-13
+
+
+def test_gemm_linearity_at_scale(lib):
+    """size-independent property at a size the CPU oracle cannot do in seconds: A(x+y) = Ax + Ay, (A^T)(Ax) symmetric."""
+    m, n, l = 40000, 8192, 264
+    A = torch.randn((n, m), dtype=torch.float64, device="cuda")
+    X = torch.randn((l, n), dtype=torch.float64, device="cuda")
+    Y = torch.randn((l, n), dtype=torch.float64, device="cuda")
+    out = [torch.empty((l, m), dtype=torch.float64, device="cuda") for _ in range(3)]
+    for B, Cm in zip((X, Y, X + Y), out):
+        D.gemm("N", "N", m, l, n, A, m, B, n, Cm, m)
+    sync(lib)
+    assert ((out[0] + out[1] - out[2]).abs().max() / out[2].abs().max()).item() < 1e-13
+    G = torch.empty((l, l), dtype=torch.float64, device="cuda")
+    D.gemm("T", "N", l, l, m, out[0], m, out[0], m, G, l)
+    sync(lib)
+    assert ((G - G.t()).abs().max() / G.abs().max()).item() < 1e-13
+
+
+@pytest.mark.parametrize("m,l,cond,force", [(5000, 120, 1e3, 0), (5000, 120, 1e12, 0), (3000, 200, 1e2, 1), (20000, 520, 1e5, 0),
+                                            (64, 64, 10, 0), (1000, 1, 1, 0)])
+def test_orthonormalize(lib, m, l, cond, force):
+    rng = np.random.default_rng(3)
+    Q0, _ = np.linalg.qr(rng.standard_normal((m, l)))
+    W, _ = np.linalg.qr(rng.standard_normal((l, l)))
+    Y = (Q0 * np.logspace(0, -np.log10(cond), l)) @ W.T
+    Yd = D.from_numpy_cm(Y)
+    R = torch.zeros((l, l), dtype=torch.float64, device="cuda")
+    lib.rsvd_b200_set_option(b"force_qr_fallback", force)
+    native.check(lib.rsvd_b200_orthonormalize(Yd.data_ptr(), m, m, l, R.data_ptr(), l))
+    sync(lib)
+    lib.rsvd_b200_set_option(b"force_qr_fallback", 0)
+    path = lib.rsvd_b200_get_option(b"last_qr_path")
+    assert path == (2 if (force or cond > 1e8) else 1)
+    Q, Rn = D.to_numpy(Yd), R.t().cpu().numpy()
+    assert np.abs(Q.T @ Q - np.eye(l)).max() < 1e-13
+    assert np.linalg.norm(Q @ Rn - Y) / np.linalg.norm(Y) < 1e-13
+    assert np.abs(np.tril(Rn, -1)).max() == 0.0
+    # same range as Householder QR
+    Qh, _ = np.linalg.qr(Y)
+    if cond < 1e10:
+        assert np.linalg.norm(Q - Qh @ (Qh.T @ Q)) < 1e-6
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 33, 120, 520])
+def test_jacobi_svd_and_eig(lib, n):
+    rng = np.random.default_rng(n)
+    U0, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    V0, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    s0 = np.logspace(0, -5, n) if n > 1 else np.array([2.5])
+    A = (U0 * s0) @ V0.T
+    Ad = D.from_numpy_cm(A)
+    U = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    Vt = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    s = torch.empty(n, dtype=torch.float64, device="cuda")
+    native.check(lib.rsvd_b200_svd_small(Ad.data_ptr(), n, n, U.data_ptr(), n, s.data_ptr(), Vt.data_ptr(), n))
+    sync(lib)
+    sn, Un, Vtn = s.cpu().numpy(), U.t().cpu().numpy(), Vt.t().cpu().numpy()
+    assert np.max(np.abs(sn - s0) / s0) < 1e-10
+    assert np.all(np.diff(sn) <= 0)
+    assert np.linalg.norm((Un * sn) @ Vtn - A) / np.linalg.norm(A) < 1e-13
+    assert np.abs(Un.T @ Un - np.eye(n)).max() < 1e-12 and np.abs(Vtn @ Vtn.T - np.eye(n)).max() < 1e-12
+    # symmetric PSD eigenproblem (B B^T of the vnum=2 branch): ascending eigenvalues like dsyev
+    S = (V0 * s0 ** 2) @ V0.T
+    S = (S + S.T) / 2
+    Sd = D.from_numpy_cm(S)
+    w = torch.empty(n, dtype=torch.float64, device="cuda")
+    native.check(lib.rsvd_b200_eig_small(Sd.data_ptr(), n, n, w.data_ptr()))
+    sync(lib)
+    wn, Vn = w.cpu().numpy(), D.to_numpy(Sd)
+    assert np.all(np.diff(wn) >= 0)
+    assert np.max(np.abs(wn[::-1] - s0 ** 2) / (s0 ** 2).max()) < 1e-14
+    assert np.linalg.norm(S @ Vn - Vn * wn) / np.linalg.norm(S) < 1e-13
+
+
+@pytest.mark.parametrize("m,n", [(12, 40), (120, 1500), (100, 2000), (300, 5000), (40, 40), (7, 3), (200, 9000)])
+def test_geqp3_pivots_bit_exact_vs_lapack(lib, m, n):
+    from scipy.linalg import lapack
+    rng = np.random.default_rng(m + n)
+    r = min(m, n, 60)
+    Y = rng.standard_normal((m, r)) @ (np.logspace(0, -5, r)[:, None] * rng.standard_normal((r, n)))
+    Y = Y + 1e-9 * rng.standard_normal((m, n))
+    Yd = D.from_numpy_cm(Y)
+    jp = torch.empty(n, dtype=torch.float64, device="cuda")
+    native.check(lib.rsvd_b200_geqp3(Yd.data_ptr(), m, m, n, jp.data_ptr()))
+    sync(lib)
+    qr, jpvt, tau, _, info = lapack.dgeqp3(np.asfortranarray(Y))
+    assert np.array_equal(jp.cpu().numpy().astype(int), jpvt - 1)
+    k = min(m, n)
+    Rg, Rr = np.triu(D.to_numpy(Yd)[:k, :]), np.triu(qr[:k, :])
+    assert np.abs(np.abs(Rg) - np.abs(Rr)).max() < 1e-11 * np.abs(Rr).max()
+    d = np.abs(np.diag(Rg))
+    assert np.all(d[:-1] >= d[1:] * (1 - 1e-12))     # non-increasing |R_ii|: the pivoting property
+
+
+def test_trsm_and_lu_solve(lib):
+    rng = np.random.default_rng(0)
+    k, nc = 300, 2000
+    R = np.triu(rng.standard_normal((k, k))) + 5 * np.eye(k)
+    B = rng.standard_normal((k, nc))
+    Rd, Bd = D.from_numpy_cm(R), D.from_numpy_cm(B)
+    native.check(lib.rsvd_b200_trsm_left_upper(Rd.data_ptr(), k, k, Bd.data_ptr(), k, nc))
+    sync(lib)
+    X = D.to_numpy(Bd)
+    assert np.linalg.norm(R @ X - B) / np.linalg.norm(B) < 1e-13
+    A = rng.standard_normal((k, k))
+    Ad, Bd = D.from_numpy_cm(A), D.from_numpy_cm(B[:, :k])
+    native.check(lib.rsvd_b200_lu_solve(Ad.data_ptr(), k, k, Bd.data_ptr(), k, k))
+    sync(lib)
+    X = D.to_numpy(Bd)
+    assert np.linalg.norm(A @ X - B[:, :k]) / np.linalg.norm(B[:, :k]) < 1e-11
+
+
+def test_device_resident_svd_roundtrip_at_scale(lib):
+    """Device-resident entry point on a matrix generated in HBM with a KNOWN spectrum (no CPU oracle at this size):
+    sigma must match the construction, U/V orthonormal, streamed residual ~ the discarded tail."""
+    m, n, k, p = 30000, 12000, 200, 20
+    g = torch.Generator(device="cuda").manual_seed(0)
+    X, _ = torch.linalg.qr(torch.randn((m, k + 50), dtype=torch.float64, device="cuda", generator=g))
+    W, _ = torch.linalg.qr(torch.randn((n, k + 50), dtype=torch.float64, device="cuda", generator=g))
+    sig = torch.cat([torch.logspace(0, -4, k, dtype=torch.float64), 1e-9 * torch.ones(50, dtype=torch.float64)]).cuda()
+    A_cm = ((X * sig) @ W.t()).t().contiguous()     # (n, m) tensor == column-major m x n
+    torch.cuda.synchronize()
+    U, S, V = D.svd_rand(A_cm, k, p, 1, 2, 1, seed=777)
+    pe = lib.rsvd_b200_svd_percent_error_dev(A_cm.data_ptr(), m, n, m, U.data_ptr(), m, S.data_ptr(), V.data_ptr(), n, k)
+    sync(lib)
+    assert ((S - sig[:k]).abs() / sig[:k]).max().item() < 1e-9
+    assert (U @ U.t() - torch.eye(k, dtype=torch.float64, device="cuda")).abs().max().item() < 1e-11
+    assert (V @ V.t() - torch.eye(k, dtype=torch.float64, device="cuda")).abs().max().item() < 1e-11
+    expect = 100 * (sig[k:].norm() / sig.norm()).item()
+    assert pe == pytest.approx(expect, rel=0.05)
