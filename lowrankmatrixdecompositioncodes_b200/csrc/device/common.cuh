@@ -46,6 +46,7 @@ struct Ctx {
     int verbose = 0;
     int force_generic_gemm = 0;
     int force_qr_fallback = 0;
+    int jacobi_transpose = 0;        // run the one-sided Jacobi on R^T (lower triangular) instead of R
     int last_qr_path = 0;            // 1 = CholeskyQR2, 2 = TSQR-preconditioned fallback
     unsigned long long qr_fallbacks = 0;
 };

@@ -4,35 +4,38 @@
 // (cblas_dgemm NN / TN call sites matrix_vector_functions_intel_mkl.c:542,551, as used by RRA:95,108,120,139.)
 //
 // Design (sm_100a):
-//   * tcgen05.mma has no f64 kind, so the FP64 tensor path is warp-level DMMA (mma.sync m8n8k4.f64).
-//   * CTA tile 128 x 128 x 16, 5-stage smem ring filled by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B,
-//     16-double-wide boxes => out-of-range rows/cols/k are zero-filled by hardware), mbarrier full/empty pairs.
+//   * tcgen05.mma has no f64 kind, so the FP64 tensor path is warp-level DMMA (mma.sync m8n8k4.f64 -> DMMA.8x8x4).
+//   * CTA tile 128 x (8*NB) x 16 with NB <= 16 column groups chosen per call so that the n-tiles cover n = k+p
+//     without padding waste (l = 520 -> 5 tiles of 104 columns, not 5 x 128).  5-stage smem ring filled by TMA
+//     (cp.async.bulk.tensor.2d, SWIZZLE_128B, 16-double-wide boxes => out-of-range rows/cols/k are zero-filled by
+//     hardware), mbarrier full/empty pairs.
 //   * warp-specialised: warpgroup 0 = producer (one lane issues TMA; in sketch mode all 128 threads generate the
-//     Omega tile with Philox4x32-10 + Box-Muller straight into the swizzled smem stage, Omega never exists in
-//     HBM), warpgroups 1-2 = 8 DMMA consumer warps, each a 64 x 32 sub-tile (64 accumulator doubles/thread).
+//     Omega tile with Philox4x32-10 + Box-Muller straight into the swizzled smem stage — Omega never exists in HBM),
+//     warpgroups 1-2 = 8 DMMA consumer warps, each 16 rows x all 8*NB columns (<= 64 accumulator doubles/thread).
 //     setmaxnreg moves registers from the producer to the consumers.
-//   * fragment loads are LDS.128 and bank-conflict free under the 128B swizzle by construction:
+//   * fragment loads are LDS.128 and bank-conflict free under the 128B swizzle by construction (ncu: 1e4 conflicts
+//     in 1.9e9 wavefronts):
 //       K-major operand tile [row][16 k]: thread (g,t) reads chunk (t+4s') of physical row pi(g) = (g>>1)+4(g&1),
 //         i.e. k = 2t+8s'+{0,1} (two consecutive DMMA k-steps per load);
 //       M-major operand tile [k][16 m]:   thread (g,t) reads chunk g of row k = 2t+c+8s', i.e. rows 2g, 2g+1
 //         (two DMMA row-blocks per load).
 //     Both use the same k permutation kappa(t) = 2t+c+8s', which is legal because the k-sum is order-free.
-//   * split-K over gridDim.y with a deterministic second-pass reduction when the tile count under-fills 148 SMs.
+//   * work units = (tile, k-split).  Under-filled grids split every tile along k; otherwise only the tiles of the
+//     last partial wave are split so that all 148 SMs finish together.  Split tiles write partial sums to a
+//     workspace and a second kernel adds them in fixed order (deterministic, no atomics).
 #include "common.cuh"
 
 namespace rsvd {
 
-void splitk_reduce(const double *part, int splits, i64 m, i64 n, double alpha, double beta, double *C, i64 ldc,
-                   int batch, i64 sC);
-
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int BM = 128, BK = 16, BN_MAX = 128;
 constexpr int STAGES = 5;
-constexpr int A_STAGE_BYTES = BM * BK * 8;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 8;   // 16 KB
+constexpr int A_STAGE_BYTES = BM * BK * 8;       // 16 KB
+constexpr int B_STAGE_BYTES = BN_MAX * BK * 8;   // 16 KB
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int NTHREADS = 384;
+constexpr int PART_TILE = BM * BN_MAX;           // doubles per partial tile
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -71,8 +74,12 @@ struct TmaP {
     i64 m, n, k;          // C is m x n, contraction length k
     double *C; i64 ldc;
     double alpha, beta;
-    int tiles_n;          // n-tiles (fastest-varying in blockIdx.x)
-    int splits; int iters_per_split; double *part;
+    int tiles_n;          // n-tiles (fastest-varying in the tile index)
+    int nb_tile;          // column groups (of 8) per n-tile
+    int total_iters;      // ceil(k / BK)
+    int main_tiles, s_main, s_tail;   // tiles [0,main_tiles) are split s_main ways, the rest s_tail ways
+    double *part;         // partial tiles of split units
+    int c_vec2;           // C rows can be stored as 16-byte pairs
     uint64_t seed; i64 ph_sk, ph_sc, ph_off;
 };
 
@@ -109,9 +116,24 @@ __device__ __forceinline__ void lds128(uint32_t addr, double &x, double &y) {
 __device__ __forceinline__ void sts128(uint32_t addr, double x, double y) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
 }
+__device__ __forceinline__ void sts64(uint32_t addr, double x) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(x) : "memory");
+}
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// byte offset of element (column j, k index kk) inside a K-major [col][16 k] stage under SWIZZLE_128B
+__device__ __forceinline__ uint32_t bswz(int j, int kk) {
+    return (uint32_t)(j * 128 + ((((kk >> 1) ^ (j & 7))) << 4) + (kk & 1) * 8);
+}
+
+// unit -> (tile, split, nsplit)
+__device__ __forceinline__ void decode_unit(const TmaP &p, int unit, int &tile, int &split, int &nsplit) {
+    const int main_units = p.main_tiles * p.s_main;
+    if (unit < main_units) { tile = unit / p.s_main; split = unit - tile * p.s_main; nsplit = p.s_main; }
+    else { int u = unit - main_units; int tt = u / p.s_tail; tile = p.main_tiles + tt; split = u - tt * p.s_tail; nsplit = p.s_tail; }
 }
 
 // A_KMAJOR: op(A) = A^T with A stored k x m (TN); otherwise A stored m x k (NN).  PHILOX: B generated on the fly.
@@ -128,12 +150,16 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int tile_n = blockIdx.x % p.tiles_n, tile_m = blockIdx.x / p.tiles_n;
-    const i64 m0 = (i64)tile_m * BM, n0 = (i64)tile_n * BN;
-    const int total_iters = (int)((p.k + BK - 1) / BK);
-    const int it0 = blockIdx.y * p.iters_per_split;
-    const int it1 = min(total_iters, it0 + p.iters_per_split);
-    const int niter = max(0, it1 - it0);
+    int tile, split, nsplit;
+    decode_unit(p, (int)blockIdx.x, tile, split, nsplit);
+    const int tile_n = tile % p.tiles_n, tile_m = tile / p.tiles_n;
+    const i64 m0 = (i64)tile_m * BM, n0 = (i64)tile_n * (8 * p.nb_tile);
+    // column groups of this tile that hold real columns (the last n-tile may be narrower)
+    const int NB = (int)min((i64)p.nb_tile, (p.n - n0 + 7) / 8);
+    const int ips = (p.total_iters + nsplit - 1) / nsplit;
+    const int it0 = split * ips;
+    const int niter = max(0, min(p.total_iters, it0 + ips) - it0);
+    const uint32_t b_bytes = (uint32_t)(p.nb_tile * 8 * BK * 8);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -155,7 +181,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const int kc = (it0 + it) * BK;
                 if (tid == 0) {
                     const uint32_t fb = full_bar(s);
-                    mbar_expect_tx(fb, PHILOX ? A_STAGE_BYTES : (A_STAGE_BYTES + B_STAGE_BYTES));
+                    mbar_expect_tx(fb, PHILOX ? A_STAGE_BYTES : (A_STAGE_BYTES + b_bytes));
                     if (A_KMAJOR) {
                         tma_load_2d(sA + s * A_STAGE_BYTES, &mapA, kc, (int)m0, fb);
                     } else {
@@ -166,49 +192,58 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     if (!PHILOX) tma_load_2d(sB + s * B_STAGE_BYTES, &mapB, kc, (int)n0, fb);
                 }
                 if (PHILOX) {
-                    // Omega tile: element (col j, kk) = normal(seed, off + (kc+kk)*sk + (n0+j)*sc),
-                    // stored at j*128 + (((kk>>1) ^ (j&7))<<4) + (kk&1)*8 (the TMA SWIZZLE_128B image of [col][16 k]).
+                    // Omega tile: element (col j, kk) = normal(seed, off + (kc+kk)*sk + (n0+j)*sc), written at bswz(j, kk)
+                    // (the image a TMA SWIZZLE_128B load of a stored Omega would have produced).
                     const uint32_t bbase = sB + s * B_STAGE_BYTES;
-                    uint64_t cached_blk = ~0ull;
-                    float z[4];
+                    const int ncols = 8 * NB;
                     if (p.ph_sk == 1) {
-                        const int j = tid;   // 0..127 : one column, 16 consecutive linear entries
-                        const uint64_t lin0 = (uint64_t)(p.ph_off + (i64)kc + (n0 + j) * p.ph_sc);
+                        // linear index runs along k: thread = column, its 16 entries are 4 aligned Philox blocks
+                        const int j = tid;
+                        if (j < ncols) {
+                            const uint64_t lin0 = (uint64_t)(p.ph_off + (i64)kc + (n0 + j) * p.ph_sc);
+                            if ((lin0 & 3u) == 0) {
+                                float z[4][4];
 #pragma unroll
-                        for (int kp = 0; kp < 8; ++kp) {
-                            double v[2];
+                                for (int qd = 0; qd < 4; ++qd) rsvd_normal4(p.seed, (lin0 >> 2) + qd, z[qd]);   // 4 independent chains
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                uint64_t lin = lin0 + (uint64_t)(2 * kp + h);
-                                uint64_t blk = lin >> 2;
-                                if (blk != cached_blk) { rsvd_normal4(p.seed, blk, z); cached_blk = blk; }
-                                uint32_t sel = (uint32_t)lin & 3u;
-                                float f = sel == 0 ? z[0] : (sel == 1 ? z[1] : (sel == 2 ? z[2] : z[3]));
-                                v[h] = (double)f;
+                                for (int qd = 0; qd < 4; ++qd) {
+                                    sts128(bbase + j * 128 + (((2 * qd) ^ (j & 7)) << 4), (double)z[qd][0], (double)z[qd][1]);
+                                    sts128(bbase + j * 128 + (((2 * qd + 1) ^ (j & 7)) << 4), (double)z[qd][2], (double)z[qd][3]);
+                                }
+                            } else {
+                                uint64_t cached = ~0ull;
+                                float z[4];
+                                for (int kk = 0; kk < 16; ++kk) {
+                                    uint64_t lin = lin0 + (uint64_t)kk;
+                                    if ((lin >> 2) != cached) { cached = lin >> 2; rsvd_normal4(p.seed, cached, z); }
+                                    uint32_t sel = (uint32_t)lin & 3u;
+                                    float f = sel == 0 ? z[0] : (sel == 1 ? z[1] : (sel == 2 ? z[2] : z[3]));
+                                    sts64(bbase + bswz(j, kk), (double)f);
+                                }
                             }
-                            sts128(bbase + j * 128 + ((kp ^ (j & 7)) << 4), v[0], v[1]);
+                        }
+                    } else if (p.ph_sc == 1 && ((p.ph_sk | (p.ph_off + n0)) & 3) == 0) {
+                        // linear index runs along the columns (left sketch of the ID): item = (k, column quad)
+                        const int nitems = 16 * 2 * NB;    // 16 k  x  ncols/4 quads
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int item = tid + r * 128;
+                            if (item < nitems) {
+                                const int kk = item & 15, cq = item >> 4;
+                                const uint64_t lin = (uint64_t)(p.ph_off + ((i64)kc + kk) * p.ph_sk + n0 + 4 * cq);
+                                float z[4];
+                                rsvd_normal4(p.seed, lin >> 2, z);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) sts64(bbase + bswz(4 * cq + i, kk), (double)z[i]);
+                            }
                         }
                     } else {
-                        // consecutive linear entries run along the columns (ph_sc == 1) or arbitrary strides:
-                        // thread owns k-pair kp = tid&7 and columns (tid>>3)*8 .. +7
-                        const int kp = tid & 7, jb = (tid >> 3) * 8;
-                        double v[8][2];
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const i64 linb = p.ph_off + ((i64)kc + 2 * kp + h) * p.ph_sk + (n0 + jb) * p.ph_sc;
-#pragma unroll
-                            for (int jj = 0; jj < 8; ++jj) {
-                                uint64_t lin = (uint64_t)(linb + jj * p.ph_sc);
-                                uint64_t blk = lin >> 2;
-                                if (blk != cached_blk) { rsvd_normal4(p.seed, blk, z); cached_blk = blk; }
-                                uint32_t sel = (uint32_t)lin & 3u;
-                                float f = sel == 0 ? z[0] : (sel == 1 ? z[1] : (sel == 2 ? z[2] : z[3]));
-                                v[jj][h] = (double)f;
-                            }
+                        // arbitrary strides: one Philox block per element
+                        for (int e = tid; e < ncols * 16; e += 128) {
+                            const int kk = e & 15, j = e >> 4;
+                            const uint64_t lin = (uint64_t)(p.ph_off + ((i64)kc + kk) * p.ph_sk + (n0 + j) * p.ph_sc);
+                            sts64(bbase + bswz(j, kk), (double)rsvd_normal_at(p.seed, lin));
                         }
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj)
-                            sts128(bbase + (jb + jj) * 128 + ((kp ^ ((jb + jj) & 7)) << 4), v[jj][0], v[jj][1]);
                     }
                     mbar_arrive(full_bar(s));
                 }
@@ -217,64 +252,61 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     } else {
         // ===================== consumer warpgroups =====================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-        const int cw = warp - 4;
-        const int wm = cw & 1, wn = cw >> 1;      // 2 x 4 warps, warp tile 64 (m) x 32 (n)
+        const int cw = warp - 4;                  // rows [16*cw, 16*cw+16) of the tile, all columns
         const int g = lane >> 2, t = lane & 3;
         const int pg = (g >> 1) + 4 * (g & 1);    // physical row of logical row g in a K-major 8-row group
 
-        double acc[8][4][2];
+        double acc[2][16][2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < 16; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-        // loop-invariant byte offsets inside a stage
-        uint32_t boff[4][2];   // B: [col-group][s']
+        // loop-invariant byte offsets inside a stage (s' = 0; s' = 1 adds 64 bytes before the XOR -> recomputed below)
+        const uint32_t b_row = (uint32_t)(pg * 128);
+        uint32_t b_ch[2], a_off[2][2];
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
+        for (int sp = 0; sp < 2; ++sp) {
+            b_ch[sp] = (uint32_t)(((t + 4 * sp) ^ pg) << 4);
 #pragma unroll
-            for (int sp = 0; sp < 2; ++sp)
-                boff[nb][sp] = (uint32_t)((wn * 32 + nb * 8 + pg) * 128 + (((t + 4 * sp) ^ pg) << 4));
+            for (int c = 0; c < 2; ++c) {
+                if (A_KMAJOR) a_off[sp][c] = (uint32_t)((cw * 16 + c * 8 + pg) * 128) + b_ch[sp];      // c = row-block here
+                else { const int kk = 2 * t + c + 8 * sp; a_off[sp][c] = (uint32_t)(cw * 2048 + kk * 128 + ((g ^ (kk & 7)) << 4)); }
+            }
+        }
 
         for (int it = 0; it < niter; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (uint32_t)((it / STAGES) & 1);
             mbar_wait(full_bar(s), ph);
             const uint32_t a_base = sA + s * A_STAGE_BYTES;
-            const uint32_t b_base = sB + s * B_STAGE_BYTES;
+            const uint32_t b_base = sB + s * B_STAGE_BYTES + b_row;
 #pragma unroll
             for (int sp = 0; sp < 2; ++sp) {
-                double b[4][2];
-#pragma unroll
-                for (int nb = 0; nb < 4; ++nb) lds128(b_base + boff[nb][sp], b[nb][0], b[nb][1]);
+                // a[x][c]: x = row-block (0/1), c = k-step within the pair
+                double a[2][2];
                 if (A_KMAJOR) {
-                    double a[8][2];
-#pragma unroll
-                    for (int rb = 0; rb < 8; ++rb)
-                        lds128(a_base + (uint32_t)((wm * 64 + rb * 8 + pg) * 128 + (((t + 4 * sp) ^ pg) << 4)),
-                               a[rb][0], a[rb][1]);
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int rb = 0; rb < 8; ++rb)
-#pragma unroll
-                            for (int nb = 0; nb < 4; ++nb) dmma(acc[rb][nb][0], acc[rb][nb][1], a[rb][c], b[nb][c]);
+                    lds128(a_base + a_off[sp][0], a[0][0], a[0][1]);
+                    lds128(a_base + a_off[sp][1], a[1][0], a[1][1]);
                 } else {
+                    lds128(a_base + a_off[sp][0], a[0][0], a[1][0]);   // k-step c=0: rows 2g (block 0), 2g+1 (block 1)
+                    lds128(a_base + a_off[sp][1], a[0][1], a[1][1]);   // k-step c=1
+                }
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int kk = 2 * t + c + 8 * sp;
-                        double a[4][2];
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    if (q4 * 4 < NB) {
+                        double b[4][2];
 #pragma unroll
-                        for (int mc = 0; mc < 4; ++mc)
-                            lds128(a_base + (uint32_t)((wm * 4 + mc) * 2048 + kk * 128 + ((g ^ (kk & 7)) << 4)),
-                                   a[mc][0], a[mc][1]);
+                        for (int i = 0; i < 4; ++i)
+                            if (q4 * 4 + i < NB) lds128(b_base + (uint32_t)((q4 * 4 + i) * 1024) + b_ch[sp], b[i][0], b[i][1]);
 #pragma unroll
-                        for (int mc = 0; mc < 4; ++mc)
+                        for (int c = 0; c < 2; ++c)
 #pragma unroll
-                            for (int xy = 0; xy < 2; ++xy)
-#pragma unroll
-                                for (int nb = 0; nb < 4; ++nb)
-                                    dmma(acc[mc * 2 + xy][nb][0], acc[mc * 2 + xy][nb][1], a[mc][xy], b[nb][c]);
+                            for (int i = 0; i < 4; ++i)
+                                if (q4 * 4 + i < NB) {
+                                    dmma(acc[0][q4 * 4 + i][0], acc[0][q4 * 4 + i][1], a[0][c], b[i][c]);
+                                    dmma(acc[1][q4 * 4 + i][0], acc[1][q4 * 4 + i][1], a[1][c], b[i][c]);
+                                }
                     }
                 }
             }
@@ -282,36 +314,92 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (lane == 0) mbar_arrive(empty_bar(s));
         }
 
-        // ---- epilogue: accumulators -> C (or split-K partial) ----
-        const bool partial = p.splits > 1;
-        double *Cb = partial ? p.part + (i64)blockIdx.y * p.m * p.n : p.C;
-        const i64 ldc = partial ? p.m : p.ldc;
-        const double alpha = partial ? 1.0 : p.alpha, beta = partial ? 0.0 : p.beta;
+        // ---- epilogue: accumulators -> C, or the unit's partial tile ----
+        // accumulator acc[x][nb][cc]: row = 16*cw + (M-major: 2g + x | K-major: 8x + pg), col = 8*nb + t + 4*cc
+        if (nsplit > 1) {
+            double *P = p.part + (i64)blockIdx.x * PART_TILE;
 #pragma unroll
-        for (int rb = 0; rb < 8; ++rb) {
-            // physical row of accumulator row-block rb, logical row g
-            i64 row;
-            if (A_KMAJOR) row = m0 + wm * 64 + rb * 8 + pg;
-            else          row = m0 + wm * 64 + (rb >> 1) * 16 + 2 * g + (rb & 1);
-            if (row >= p.m) continue;
+            for (int nb = 0; nb < 16; ++nb)
+                if (nb < NB)
 #pragma unroll
-            for (int nb = 0; nb < 4; ++nb)
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int col = nb * 8 + t + 4 * cc;
+                        if (A_KMAJOR) {
+                            P[col * BM + cw * 16 + pg] = acc[0][nb][cc];
+                            P[col * BM + cw * 16 + 8 + pg] = acc[1][nb][cc];
+                        } else {
+                            *reinterpret_cast<double2 *>(P + col * BM + cw * 16 + 2 * g) = make_double2(acc[0][nb][cc], acc[1][nb][cc]);
+                        }
+                    }
+        } else {
+            const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    // logical column 2t+cc -> physical column pi(2t+cc) = t + 4*cc
-                    i64 col = n0 + wn * 32 + nb * 8 + t + 4 * cc;
-                    if (col >= p.n) continue;
-                    double v = alpha * acc[rb][nb][cc];
-                    double *c = Cb + col * ldc + row;
-                    if (beta != 0.0) v += beta * (*c);
-                    *c = v;
-                }
+            for (int nb = 0; nb < 16; ++nb)
+                if (nb < NB)
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const i64 col = n0 + nb * 8 + t + 4 * cc;
+                        if (col >= p.n) continue;
+                        double *cp = p.C + col * p.ldc;
+                        if (A_KMAJOR) {
+#pragma unroll
+                            for (int x = 0; x < 2; ++x) {
+                                const i64 row = m0 + cw * 16 + 8 * x + pg;
+                                if (row < p.m) {
+                                    double v = alpha * acc[x][nb][cc];
+                                    if (beta != 0.0) v += beta * cp[row];
+                                    cp[row] = v;
+                                }
+                            }
+                        } else {
+                            const i64 row = m0 + cw * 16 + 2 * g;
+                            if (p.c_vec2 && row + 1 < p.m) {
+                                double2 v = make_double2(alpha * acc[0][nb][cc], alpha * acc[1][nb][cc]);
+                                double2 *dst = reinterpret_cast<double2 *>(cp + row);
+                                if (beta != 0.0) { double2 o = *dst; v.x += beta * o.x; v.y += beta * o.y; }
+                                *dst = v;
+                            } else {
+#pragma unroll
+                                for (int x = 0; x < 2; ++x)
+                                    if (row + x < p.m) {
+                                        double v = alpha * acc[x][nb][cc];
+                                        if (beta != 0.0) v += beta * cp[row + x];
+                                        cp[row + x] = v;
+                                    }
+                            }
+                        }
+                    }
         }
     }
 }
 
+// sums the partial tiles of split units in fixed order: C = alpha * sum_s P[s] + beta * C.  One CTA per split tile.
+__global__ void __launch_bounds__(256) tile_reduce_kernel(TmaP p, int first_split_tile_is_main) {
+    // split tiles: if s_main > 1 all main tiles (index 0..main_tiles-1) come first, then the tail tiles
+    int st = blockIdx.x, tile, nsplit, unit0;
+    const int n_main_split = (p.s_main > 1) ? p.main_tiles : 0;
+    if (st < n_main_split) { tile = st; nsplit = p.s_main; unit0 = tile * p.s_main; }
+    else { int tt = st - n_main_split; tile = p.main_tiles + tt; nsplit = p.s_tail; unit0 = p.main_tiles * p.s_main + tt * p.s_tail; }
+    (void)first_split_tile_is_main;
+    const int tile_n = tile % p.tiles_n, tile_m = tile / p.tiles_n;
+    const i64 m0 = (i64)tile_m * BM, n0 = (i64)tile_n * (8 * p.nb_tile);
+    const int ncols = (int)min((i64)(8 * p.nb_tile), p.n - n0);
+    const double *P = p.part + (i64)unit0 * PART_TILE;
+    for (int e = threadIdx.x; e < ncols * BM; e += blockDim.x) {
+        const int r = e % BM, c = e / BM;
+        const i64 row = m0 + r, col = n0 + c;
+        if (row >= p.m) continue;
+        double s = 0.0;
+        for (int u = 0; u < nsplit; ++u) s += P[(i64)u * PART_TILE + c * BM + r];
+        double *dst = p.C + col * p.ldc + row;
+        double v = p.alpha * s;
+        if (p.beta != 0.0) v += p.beta * (*dst);
+        *dst = v;
+    }
+}
+
 template <bool AK, bool PH>
-bool launch(const CUtensorMap &ma, const CUtensorMap &mb, const TmaP &p, dim3 grid) {
+bool launch(const CUtensorMap &ma, const CUtensorMap &mb, const TmaP &p, unsigned grid) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<AK, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -335,13 +423,17 @@ bool gemm_tma_try(const Gemm &g) {
     if (!g.philox && (((uintptr_t)g.B & 15) || (g.ldb & 1))) return false;
     if (g.m >= (1ll << 31) || g.n >= (1ll << 31) || g.k >= (1ll << 31)) return false;
 
+    // n-tiling: G column groups of 8 spread evenly over T tiles of at most 16 groups
+    const i64 G = (g.n + 7) / 8;
+    const i64 T = (G + 15) / 16;
+    const int nb_tile = (int)((G + T - 1) / T);
+
     CUtensorMap mapA, mapB;
-    memset(&mapB, 0, sizeof(mapB));
     bool ok = ta ? make_map(&mapA, g.A, g.k, g.m, g.lda, BM)    // A stored k x m : inner k, box {16 k, 128 rows}
                  : make_map(&mapA, g.A, g.m, g.k, g.lda, BK);   // A stored m x k : inner m, box {16 m, 16 k}
     if (!ok) return false;
     if (!g.philox) {
-        if (!make_map(&mapB, g.B, g.k, g.n, g.ldb, BN)) return false;
+        if (!make_map(&mapB, g.B, g.k, g.n, g.ldb, 8 * nb_tile)) return false;
     } else {
         mapB = mapA;
     }
@@ -349,34 +441,49 @@ bool gemm_tma_try(const Gemm &g) {
     TmaP p;
     p.m = g.m; p.n = g.n; p.k = g.k; p.C = g.C; p.ldc = g.ldc; p.alpha = g.alpha; p.beta = g.beta;
     p.seed = g.seed; p.ph_sk = g.ph_sk; p.ph_sc = g.ph_sc; p.ph_off = g.ph_off;
-    const i64 tm = (g.m + BM - 1) / BM, tn = (g.n + BN - 1) / BN;
-    const i64 tiles = tm * tn;
-    if (tiles > 0x7fffffffll) return false;
-    p.tiles_n = (int)tn;
-    const int total_iters = (int)((g.k + BK - 1) / BK);
-    // split-K: pick the split count with the best wave efficiency on `sms` SMs (ties -> fewer splits)
-    int best = 1; double best_eff = 0.0;
+    p.c_vec2 = (((uintptr_t)g.C & 15) == 0 && (g.ldc & 1) == 0) ? 1 : 0;
+    const i64 tm = (g.m + BM - 1) / BM;
+    const i64 tiles = tm * T;
+    if (tiles > 0x3fffffffll) return false;
+    p.tiles_n = (int)T; p.nb_tile = nb_tile;
+    p.total_iters = (int)((g.k + BK - 1) / BK);
     const int sms = ctx().sms;
-    for (int s = 1; s <= 16; ++s) {
-        if (total_iters / s < 64 && s > 1) break;
-        double work = (double)tiles * s;
-        double waves = ceil(work / sms);
-        double eff = work / (waves * sms);
-        if (s > 1) eff *= 0.97;      // partial write + reduction pass is not free
-        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    const int max_split = max(1, min(16, p.total_iters / 32));   // keep >= 32 k-iterations per unit
+    p.main_tiles = (int)tiles; p.s_main = 1; p.s_tail = 1;
+    if (tiles < sms) {
+        // under-filled: split every tile so that ~all SMs are busy
+        int s = (int)(sms / tiles);
+        p.s_main = max(1, min(s, max_split));
+    } else {
+        const int rem = (int)(tiles % sms);
+        if (rem != 0 && rem * 4 < sms * 3 && max_split >= 2) {
+            // only the last partial wave is split: `rem` tiles -> rem * s_tail units ~ one full wave of short units
+            p.main_tiles = (int)(tiles - rem);
+            p.s_tail = max(2, min(sms / rem, min(8, max_split)));
+        }
     }
-    int ips = (total_iters + best - 1) / best;
-    int splits = (total_iters + ips - 1) / ips;
-    p.splits = splits; p.iters_per_split = ips; p.part = nullptr;
+    const i64 tail_tiles = tiles - p.main_tiles;
+    const i64 units = (i64)p.main_tiles * p.s_main + tail_tiles * p.s_tail;
+    const i64 split_units = (p.s_main > 1 ? (i64)p.main_tiles * p.s_main : 0) + (p.s_tail > 1 ? tail_tiles * p.s_tail : 0);
     DBuf part;
-    if (splits > 1) { part.alloc((size_t)splits * g.m * g.n); p.part = part.p; }
-    dim3 grid((unsigned)tiles, (unsigned)splits, 1);
+    p.part = nullptr;
+    if (split_units > 0) {
+        // partial tiles are indexed by unit id; when only the tail is split the main units do not touch the buffer,
+        // so shift the base instead of allocating their slots
+        const i64 first_split_unit = (p.s_main > 1) ? 0 : (i64)p.main_tiles * p.s_main;
+        part.alloc((size_t)(units - first_split_unit) * PART_TILE);
+        p.part = part.p - first_split_unit * PART_TILE;
+    }
     bool launched;
-    if (ta) launched = g.philox ? launch<true, true>(mapA, mapB, p, grid) : launch<true, false>(mapA, mapB, p, grid);
-    else    launched = g.philox ? launch<false, true>(mapA, mapB, p, grid) : launch<false, false>(mapA, mapB, p, grid);
+    if (ta) launched = g.philox ? launch<true, true>(mapA, mapB, p, (unsigned)units) : launch<true, false>(mapA, mapB, p, (unsigned)units);
+    else    launched = g.philox ? launch<false, true>(mapA, mapB, p, (unsigned)units) : launch<false, false>(mapA, mapB, p, (unsigned)units);
     if (!launched) return false;
-    if (splits > 1) splitk_reduce(part.p, splits, g.m, g.n, g.alpha, g.beta, g.C, g.ldc, 1, 0);
-    return true;
+    const i64 split_tiles = (p.s_main > 1 ? p.main_tiles : 0) + (p.s_tail > 1 ? tail_tiles : 0);
+    if (split_tiles > 0) {
+        tile_reduce_kernel<<<(unsigned)split_tiles, 256, 0, ctx().stream>>>(p, 0);
+        count_launch();
+    }
+    return cudaGetLastError() == cudaSuccess;
 }
 
 }  // namespace rsvd

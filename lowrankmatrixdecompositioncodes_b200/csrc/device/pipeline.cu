@@ -12,6 +12,20 @@ namespace rsvd {
 
 namespace {
 
+// verbose >= 2: synchronising phase timer (diagnostics only)
+struct Phase {
+    double t0 = 0; bool on;
+    Phase() : on(ctx().verbose >= 2) { if (on) { cudaStreamSynchronize(ctx().stream); t0 = now(); } }
+    static double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+    void lap(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(ctx().stream);
+        double t1 = now();
+        fprintf(stderr, "[rsvd_b200]   %-28s %8.3f ms\n", what, (t1 - t0) * 1e3);
+        t0 = t1;
+    }
+};
+
 inline void mm(char ta, char tb, i64 m, i64 n, i64 k, double alpha, const double *A, i64 lda, const double *B, i64 ldb,
                double beta, double *C, i64 ldc) {
     Gemm g;
@@ -70,16 +84,29 @@ int svd_from_q(const double *A, i64 m, i64 n, i64 lda, double *Q, i64 ldq, i64 l
                double *U, i64 ldu, double *S, double *V, i64 ldv) {
     Ctx &c = ctx();
     DBuf Bt((size_t)n * l);
+    Phase ph;
     mm('T', 'N', n, l, m, 1.0, A, lda, Q, ldq, 0.0, Bt.p, n);          // Bt = A^T Q   (RRA:139)  — last pass over A
     allreduce_sum(Bt.p, (size_t)n * l);
+    ph.lap("Bt = A^T Q");
     if (vnum == 1 || vnum > 2) {
         DBuf Rhat((size_t)l * l), Uhat((size_t)l * l), Vhat_t((size_t)l * l), Vhat((size_t)l * l), sv((size_t)l);
         orthonormalize(Bt.p, n, n, l, Rhat.p, l, /*sharded=*/false);      // [Qhat, Rhat] = qr(Bt)  (RRA:146); Qhat overwrites Bt
-        jacobi_svd(Rhat.p, l, l, Uhat.p, l, sv.p, Vhat_t.p, l);           // Rhat = Uhat S Vhat^T   (RRA:152)
-        transpose(Vhat_t.p, l, Vhat.p, l, l, l);
+        ph.lap("qr(Bt)");
+        if (!c.jacobi_transpose) {
+            jacobi_svd(Rhat.p, l, l, Uhat.p, l, sv.p, Vhat_t.p, l);       // Rhat = Uhat S Vhat^T   (RRA:152)
+            transpose(Vhat_t.p, l, Vhat.p, l, l, l);
+        } else {
+            // Rhat^T = U' S V'^T  =>  Rhat = V' S U'^T : Uhat = V', Vhat = U'
+            DBuf Rt((size_t)l * l);
+            transpose(Rhat.p, l, Rt.p, l, l, l);
+            jacobi_svd(Rt.p, l, l, Vhat.p, l, sv.p, Vhat_t.p, l);         // Vhat_t holds V'^T here
+            transpose(Vhat_t.p, l, Uhat.p, l, l, l);
+        }
+        ph.lap("jacobi svd(Rhat)");
         mm('N', 'N', m, k, l, 1.0, Q, ldq, Vhat.p, l, 0.0, U, ldu);       // U = Q Vhat, first k columns (RRA:156,171)
         mm('N', 'N', n, k, l, 1.0, Bt.p, n, Uhat.p, l, 0.0, V, ldv);      // V = Qhat Uhat          (RRA:160,172)
         copy_matrix(sv.p, l, S, k, k, 1);
+        ph.lap("form U, V");
     } else {
         // eig of B B^T (RRA:175-225): B = Q^T A = Bt^T, so B B^T = Bt^T Bt
         DBuf BBt((size_t)l * l), w((size_t)l), X((size_t)l * k);
@@ -107,17 +134,24 @@ int svd_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int vnum, int
     const i64 l = k + p;
     if (k <= 0 || p < 0 || l > n || s <= 0) { set_error("rsvd_b200: invalid parameters k=%lld p=%lld s=%d (need 0 < k+p <= n, s > 0)", (long long)k, (long long)p, s); return 1; }
     DBuf Y((size_t)m * l), Z((size_t)n * l);
+    Phase ph;
     if (omega) mm('N', 'N', m, l, n, 1.0, A, lda, omega, n, 0.0, Y.p, m);           // Y = M RN (RRA:95)
     else sketch('N', m, l, n, A, lda, seed, 1, n, 0, Y.p, m);                       // RN generated in the B-operand producer
+    ph.lap("Y = A Omega (sketch)");
     for (int j = 1; j < q; ++j) {                                                   // NOTE j < q (RRA:101)
         if ((2 * j - 2) % s == 0) orthonormalize(Y.p, m, m, l, nullptr, 0, true);   // RRA:106
+        ph.lap("orth(Y)");
         mm('T', 'N', n, l, m, 1.0, A, lda, Y.p, m, 0.0, Z.p, n);                    // Z = M^T Y (RRA:108/112)
         allreduce_sum(Z.p, (size_t)n * l);
+        ph.lap("Z = A^T Y");
         if ((2 * j - 1) % s == 0) orthonormalize(Z.p, n, n, l, nullptr, 0, false);  // RRA:118
+        ph.lap("orth(Z)");
         mm('N', 'N', m, l, n, 1.0, A, lda, Z.p, n, 0.0, Y.p, m);                    // Y = M Z (RRA:120/124)
+        ph.lap("Y = A Z");
     }
     Z.release();
     orthonormalize(Y.p, m, m, l, nullptr, 0, true);                                 // Q (RRA:129-130)
+    ph.lap("Q = orth(Y)");
     return svd_from_q(A, m, n, lda, Y.p, m, l, k, vnum, U, ldu, S, V, ldv);
 }
 

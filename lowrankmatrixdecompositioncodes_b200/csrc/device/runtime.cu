@@ -206,6 +206,7 @@ void rsvd_b200_set_option(const char *name, rsvd_i64 value) {
     else if (!strcmp(name, "force_generic_gemm")) ctx().force_generic_gemm = (int)value;
     else if (!strcmp(name, "force_qr_fallback")) ctx().force_qr_fallback = (int)value;
     else if (!strcmp(name, "row0")) ctx().row0 = value;
+    else if (!strcmp(name, "jacobi_transpose")) ctx().jacobi_transpose = (int)value;
     else if (!strcmp(name, "m_global")) ctx().m_global = value;
     else set_error("rsvd_b200_set_option: unknown option '%s'", name);
 }

@@ -75,14 +75,23 @@ void low_rank_svd_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t vnum, i
         *U = matrix_new(m, max(k, 0)); *S = matrix_new(max(k, 0), max(k, 0)); *V = matrix_new(n, max(k, 0));
         return;
     }
+    struct timeval t0, t1, t2, t3;
+    gettimeofday(&t0, NULL);
     double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
     double *dU = rsvd_b200_dev_alloc((rsvd_i64)m * k), *dS = rsvd_b200_dev_alloc(k), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * k);
+    gettimeofday(&t1, NULL);
     if (dA && dU && dS && dV)
         rsvd_b200_svd_rand_dev(dA, m, n, m, k, p, (int)vnum, (int)q, (int)s, omega_seed(), NULL, dU, m, dS, dV, n);
+    rsvd_b200_sync();
+    gettimeofday(&t2, NULL);
     rsvd_b200_dev_free(dA);
     *U = download_mat(dU, m, k);
     *S = diag_from_device(dS, k);
     *V = download_mat(dV, n, k);
+    gettimeofday(&t3, NULL);
+    if (verbose())
+        fprintf(stderr, "[rsvd_b200 api] upload %.3f s (%.1f GB/s), device %.3f s, alloc+download %.3f s\n", get_seconds_frac(t0, t1),
+                8e-9 * (double)m * (double)n / get_seconds_frac(t0, t1), get_seconds_frac(t1, t2), get_seconds_frac(t2, t3));
     rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dS); rsvd_b200_dev_free(dV);
     rsvd_api_sync_error();
 }

@@ -282,4 +282,47 @@ def _qb():
     print("svd_blockrand k=0 (quirk Q1): frank %d (ref %d)  max rel sigma err %.2e" % (f, fr, np.max(np.abs(np.diag(S) - np.diag(Sr)) / np.diag(Sr))))
 
 
+@section("phases")
+def _phases():
+    """phase breakdown of the BASELINE configs[1] step (device resident) and of the host API call"""
+    import ctypes as C
+    m, n, k, p = 50000, 20000, 500, 20
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.randn((m, 640), dtype=torch.float64, device="cuda", generator=gen) / m ** 0.5
+    W = torch.randn((n, 640), dtype=torch.float64, device="cuda", generator=gen) / n ** 0.5
+    A_cm = torch.matmul(W * torch.logspace(1, -3, 640, dtype=torch.float64, device="cuda"), X.t())
+    A_cm += 1e-6 * torch.randn((n, m), dtype=torch.float64, device="cuda", generator=gen)
+    del X, W
+    torch.cuda.synchronize()
+    for jt in (0, 1):
+        lib.rsvd_b200_set_option(b"jacobi_transpose", jt)
+        D.svd_rand(A_cm, k, p, 1, 2, 1, seed=777)
+        sync()
+        lib.rsvd_b200_set_option(b"verbose", 2)
+        print("--- device-resident step, jacobi_transpose=%d" % jt, flush=True)
+        U, S, V = D.svd_rand(A_cm, k, p, 1, 2, 1, seed=777)
+        sync()
+        lib.rsvd_b200_set_option(b"verbose", 0)
+        t = timeit(lambda: D.svd_rand(A_cm, k, p, 1, 2, 1, seed=777), reps=3, warm=0)
+        print("    whole step: %.2f ms  S[0]=%.6f S[-1]=%.6e" % (t * 1e3, S[0].item(), S[-1].item()), flush=True)
+    lib.rsvd_b200_set_option(b"jacobi_transpose", 0)
+    del A_cm
+    torch.cuda.empty_cache()
+    os.environ["RSVD_B200_VERBOSE"] = "1"
+    api = pkg.Api(32)
+    M = api.lib.matrix_new(m, n)
+    hA = np.ctypeslib.as_array(M.contents.d, shape=(n, m))
+    rng = np.random.default_rng(0)
+    np.matmul(rng.standard_normal((n, 32)), rng.standard_normal((32, m)), out=hA)
+    for it in range(3):
+        Um, Sm, Vm = api.PM(), api.PM(), api.PM()
+        fr = api.I(0)
+        t0 = time.time()
+        api.lib.low_rank_svd_rand_decomp_fixed_rank(M, k, p, 1, 2, 1, C.byref(fr), C.byref(Um), C.byref(Sm), C.byref(Vm))
+        print("    API call wall: %.3f s" % (time.time() - t0), flush=True)
+        for x in (Um, Sm, Vm):
+            api.lib.matrix_delete(x)
+    api.lib.matrix_delete(M)
+
+
 print("\nlaunches total:", lib.rsvd_b200_launch_count(), " status:", lib.rsvd_b200_status(), lib.rsvd_b200_last_error())
