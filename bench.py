@@ -300,15 +300,11 @@ def main():
     # ---- e2e: the reference's C API with host buffers -------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        del A_cm  # the API call allocates its own device copy
-        torch.cuda.empty_cache()
         api = pkg.Api(32 if m * n < 2 ** 31 else 64)
         M = api.lib.matrix_new(m, n)           # pinned host memory (>= 64 MB)
-        hA = np.ctypeslib.as_array(M.contents.d, shape=(n, m))
-        rng = np.random.default_rng(rank)
-        Xh = rng.standard_normal((m, 64)) / np.sqrt(m_global)
-        Wh = rng.standard_normal((n, 64)) / np.sqrt(n)
-        np.matmul(Wh * np.logspace(1, -3, 64), Xh.T, out=hA)
+        native.check(lib.rsvd_b200_d2h(C.cast(M.contents.d, C.c_void_p), A_cm.data_ptr(), m * n))   # same matrix as the device arm
+        del A_cm  # the API call allocates its own device copy
+        torch.cuda.empty_cache()
         api.set_seed(777)
         times = []
         for it in range(1 + max(1, min(args.steps, 3))):

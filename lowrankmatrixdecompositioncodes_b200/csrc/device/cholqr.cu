@@ -13,77 +13,73 @@ namespace rsvd {
 constexpr int PB = 64;   // Cholesky / inverse block size
 
 // ---- blocked upper Cholesky G = R^T R ------------------------------------------------------------------
-// factor the diagonal block in shared memory (one CTA); flag = failing column + 1 on a non-positive pivot
-__global__ void __launch_bounds__(PB * 4) potf2_kernel(double *G, i64 ldg, i64 j0, int jb, int *flag) {
-    __shared__ double S[PB][PB + 1];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < PB * PB; e += blockDim.x) {
-        int i = e % PB, j = e / PB;
-        S[i][j] = (i < jb && j < jb && i <= j) ? G[(j0 + j) * ldg + j0 + i] : 0.0;
-    }
+// Diagonal block (<= 64 x 64) in shared memory, one thread per row of L = R^T (right-looking, one barrier pair per
+// column), followed by the inverse of the block (thread j back-substitutes column j).  Outputs: R_jj in place and
+// W = R_jj^{-1} (PB x PB, ld PB) for the panel solve.  flag = failing column + 1 on a non-positive pivot.
+__global__ void __launch_bounds__(PB) potf2_inv_kernel(double *G, i64 ldg, i64 j0, int jb, double *W, int *flag) {
+    __shared__ double L[PB][PB + 1];     // L[r][c], r >= c : lower factor (R^T)
+    __shared__ double colbuf[PB];
+    const int r = threadIdx.x;
+    for (int c = 0; c < PB; ++c) L[r][c] = (r < jb && c <= r) ? G[(j0 + r) * ldg + j0 + c] : 0.0;   // G(c, r) upper -> L(r, c)
     __syncthreads();
     for (int c = 0; c < jb; ++c) {
-        // R(c,c) = sqrt(G(c,c) - sum_{r<c} R(r,c)^2): the sums were already subtracted (right-looking inside the block)
-        double d = S[c][c];
+        double d = L[c][c];
         if (!(d > 0.0)) {
-            if (tid == 0) atomicCAS(flag, 0, (int)(j0 + c + 1));
+            if (r == 0) atomicCAS(flag, 0, (int)(j0 + c + 1));
             d = 1.0;   // keep going with finite numbers; the caller discards the result
         }
-        double r = sqrt(d);
+        const double piv = sqrt(d);
+        double lrc = 0.0;
+        if (r > c && r < jb) lrc = L[r][c] / piv;
         __syncthreads();
-        if (tid == 0) S[c][c] = r;
-        for (int j = c + 1 + tid; j < jb; j += blockDim.x) S[c][j] /= r;
+        if (r == c) L[c][c] = piv;
+        if (r > c && r < jb) { L[r][c] = lrc; colbuf[r] = lrc; }
         __syncthreads();
-        // trailing update of the block: S(i,j) -= R(c,i) R(c,j), i<=j, i>c
-        int nrem = jb - c - 1;
-        for (int e = tid; e < nrem * nrem; e += blockDim.x) {
-            int i = c + 1 + e % nrem, j = c + 1 + e / nrem;
-            if (i <= j) S[i][j] -= S[c][i] * S[c][j];
+        if (r > c && r < jb) {
+            // row r of the trailing block: L(r, k) -= L(r, c) * L(k, c) for c < k <= r
+            for (int k = c + 1; k <= r; ++k) L[r][k] -= lrc * colbuf[k];
         }
         __syncthreads();
     }
-    for (int e = tid; e < PB * PB; e += blockDim.x) {
-        int i = e % PB, j = e / PB;
-        if (i < jb && j < jb) G[(j0 + j) * ldg + j0 + i] = (i <= j) ? S[i][j] : 0.0;
-    }
-}
-
-// row panel: G(j0:j0+jb, c) <- R_jj^{-T} G(j0:j0+jb, c) for c >= j0+jb  (forward substitution, one column per thread)
-__global__ void __launch_bounds__(128) potrf_panel_kernel(double *G, i64 ldg, i64 n, i64 j0, int jb) {
-    __shared__ double S[PB][PB + 1];
-    for (int e = threadIdx.x; e < PB * PB; e += blockDim.x) {
-        int i = e % PB, j = e / PB;
-        S[i][j] = (i < jb && j < jb && i <= j) ? G[(j0 + j) * ldg + j0 + i] : 0.0;
-    }
-    __syncthreads();
-    i64 c = j0 + jb + (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    double x[PB];
-    double *col = G + c * ldg + j0;
+    // write R_jj (upper) back: R(c, r) = L(r, c)
+    for (int c = 0; c < jb; ++c)
+        if (r < jb) G[(j0 + r) * ldg + j0 + c] = (c <= r) ? L[r][c] : 0.0;
+    // inverse of R_jj: column j of X solves R x = e_j, R(i, l) = L(l, i)
+    if (r < jb) {
+        const int j = r;
+        double x[PB];
 #pragma unroll 1
-    for (int i = 0; i < jb; ++i) {
-        double s = col[i];
-        for (int r = 0; r < i; ++r) s -= S[r][i] * x[r];
-        x[i] = s / S[i][i];
+        for (int i = j; i >= 0; --i) {
+            double s = (i == j) ? 1.0 : 0.0;
+            for (int l = i + 1; l <= j; ++l) s -= L[l][i] * x[l];
+            x[i] = s / L[i][i];
+        }
+        for (int i = 0; i < PB; ++i) W[j * PB + i] = (i <= j) ? x[i] : 0.0;
+    } else {
+        for (int i = 0; i < PB; ++i) W[r * PB + i] = (i == r) ? 1.0 : 0.0;
     }
-    for (int i = 0; i < jb; ++i) col[i] = x[i];
 }
 
 int potrf_upper(double *G, i64 ldg, i64 n) {
     ensure_init();
     int *flag = ctx().d_flag;
     RSVD_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx().stream));
+    DBuf W((size_t)PB * PB), T((size_t)PB * (n > PB ? n - PB : 1));
     for (i64 j0 = 0; j0 < n; j0 += PB) {
         int jb = (int)min((i64)PB, n - j0);
-        potf2_kernel<<<1, PB * 4, 0, ctx().stream>>>(G, ldg, j0, jb, flag);
+        potf2_inv_kernel<<<1, PB, 0, ctx().stream>>>(G, ldg, j0, jb, W.p, flag);
         count_launch();
         i64 rest = n - j0 - jb;
         if (rest > 0) {
-            potrf_panel_kernel<<<(unsigned)((rest + 127) / 128), 128, 0, ctx().stream>>>(G, ldg, n, j0, jb);
-            count_launch();
-            Gemm g;   // G22 -= R12^T R12
+            // row panel: R12 = R11^{-T} G12  (GEMM with the inverted diagonal block), then G22 -= R12^T R12
+            double *G12 = G + (j0 + jb) * ldg + j0;
+            Gemm t;
+            t.ta = 'T'; t.tb = 'N'; t.m = jb; t.n = rest; t.k = jb; t.A = W.p; t.lda = PB; t.B = G12; t.ldb = ldg; t.C = T.p; t.ldc = PB;
+            gemm(t);
+            copy_matrix(T.p, PB, G12, ldg, jb, rest);
+            Gemm g;
             g.ta = 'T'; g.tb = 'N'; g.m = rest; g.n = rest; g.k = jb; g.alpha = -1.0; g.beta = 1.0;
-            g.A = G + (j0 + jb) * ldg + j0; g.lda = ldg; g.B = g.A; g.ldb = ldg;
+            g.A = G12; g.lda = ldg; g.B = G12; g.ldb = ldg;
             g.C = G + (j0 + jb) * ldg + j0 + jb; g.ldc = ldg;
             gemm(g);
         }

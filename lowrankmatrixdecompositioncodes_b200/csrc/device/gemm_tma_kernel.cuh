@@ -1,0 +1,366 @@
+// gemm_tma_kernel.cuh — kernel template of the streaming FP64 GEMM (see gemm_tma.cu for the design notes).
+#pragma once
+#include "common.cuh"
+
+namespace rsvd {
+namespace tma {
+
+
+constexpr int BM = 128, BK = 16, BN_MAX = 128;
+constexpr int STAGES = 5;
+constexpr int A_STAGE_BYTES = BM * BK * 8;       // 16 KB
+constexpr int B_STAGE_BYTES = BN_MAX * BK * 8;   // 16 KB
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NTHREADS = 384;
+constexpr int PART_TILE = BM * BN_MAX;           // doubles per partial tile
+
+struct TmaP {
+    i64 m, n, k;          // C is m x n, contraction length k
+    double *C; i64 ldc;
+    double alpha, beta;
+    int tiles_n;          // n-tiles (fastest-varying in the tile index)
+    int nb_tile;          // column groups (of 8) per n-tile
+    int total_iters;      // ceil(k / BK)
+    int main_tiles, s_main, s_tail;   // tiles [0,main_tiles) are split s_main ways, the rest s_tail ways
+    double *part;         // partial tiles of split units
+    int c_vec2;           // C rows can be stored as 16-byte pairs
+    uint64_t seed; i64 ph_sk, ph_sc, ph_off;
+};
+
+// ---- PTX helpers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, double &x, double &y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, double x) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(x) : "memory");
+}
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// byte offset of element (column j, k index kk) inside a K-major [col][16 k] stage under SWIZZLE_128B
+__device__ __forceinline__ uint32_t bswz(int j, int kk) {
+    return (uint32_t)(j * 128 + ((((kk >> 1) ^ (j & 7))) << 4) + (kk & 1) * 8);
+}
+
+// unit -> (tile, split, nsplit)
+__device__ __forceinline__ void decode_unit(const TmaP &p, int unit, int &tile, int &split, int &nsplit) {
+    const int main_units = p.main_tiles * p.s_main;
+    if (unit < main_units) { tile = unit / p.s_main; split = unit - tile * p.s_main; nsplit = p.s_main; }
+    else { int u = unit - main_units; int tt = u / p.s_tail; tile = p.main_tiles + tt; split = u - tt * p.s_tail; nsplit = p.s_tail; }
+}
+
+// A_KMAJOR: op(A) = A^T with A stored k x m (TN); otherwise A stored m x k (NN).  PHILOX: B generated on the fly.
+template <bool A_KMAJOR, bool PHILOX, int NB>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TmaP p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = smem_base;
+    const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+    const uint32_t bars = sB + STAGES * B_STAGE_BYTES;   // full[STAGES], empty[STAGES]
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    int tile, split, nsplit;
+    decode_unit(p, (int)blockIdx.x, tile, split, nsplit);
+    const int tile_n = tile % p.tiles_n, tile_m = tile / p.tiles_n;
+    const i64 m0 = (i64)tile_m * BM, n0 = (i64)tile_n * (8 * NB);
+    // NB = column groups per n-tile (compile time).  Columns beyond n in the last tile are zero-filled by TMA (or
+    // generated and never stored), so every tile runs the same branch-free inner loop.
+    const int ips = (p.total_iters + nsplit - 1) / nsplit;
+    const int it0 = split * ips;
+    const int niter = max(0, min(p.total_iters, it0 + ips) - it0);
+    constexpr uint32_t b_bytes = (uint32_t)(NB * 8 * BK * 8);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), PHILOX ? 129 : 1);
+            mbar_init(empty_bar(s), 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp < 4) {
+        // ===================== producer warpgroup =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        if (PHILOX || tid == 0) {
+            for (int it = 0; it < niter; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const int kc = (it0 + it) * BK;
+                if (tid == 0) {
+                    const uint32_t fb = full_bar(s);
+                    mbar_expect_tx(fb, PHILOX ? A_STAGE_BYTES : (A_STAGE_BYTES + b_bytes));
+                    if (A_KMAJOR) {
+                        tma_load_2d(sA + s * A_STAGE_BYTES, &mapA, kc, (int)m0, fb);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 8; ++b)
+                            tma_load_2d(sA + s * A_STAGE_BYTES + b * 2048, &mapA, (int)m0 + 16 * b, kc, fb);
+                    }
+                    if (!PHILOX) tma_load_2d(sB + s * B_STAGE_BYTES, &mapB, kc, (int)n0, fb);
+                }
+                if (PHILOX) {
+                    // Omega tile: element (col j, kk) = normal(seed, off + (kc+kk)*sk + (n0+j)*sc), written at bswz(j, kk)
+                    // (the image a TMA SWIZZLE_128B load of a stored Omega would have produced).
+                    const uint32_t bbase = sB + s * B_STAGE_BYTES;
+                    constexpr int ncols = 8 * NB;
+                    if (p.ph_sk == 1) {
+                        // linear index runs along k: thread = column, its 16 entries are 4 aligned Philox blocks
+                        const int j = tid;
+                        if (j < ncols) {
+                            const uint64_t lin0 = (uint64_t)(p.ph_off + (i64)kc + (n0 + j) * p.ph_sc);
+                            if ((lin0 & 3u) == 0) {
+                                float z[4][4];
+#pragma unroll
+                                for (int qd = 0; qd < 4; ++qd) rsvd_normal4(p.seed, (lin0 >> 2) + qd, z[qd]);   // 4 independent chains
+#pragma unroll
+                                for (int qd = 0; qd < 4; ++qd) {
+                                    sts128(bbase + j * 128 + (((2 * qd) ^ (j & 7)) << 4), (double)z[qd][0], (double)z[qd][1]);
+                                    sts128(bbase + j * 128 + (((2 * qd + 1) ^ (j & 7)) << 4), (double)z[qd][2], (double)z[qd][3]);
+                                }
+                            } else {
+                                uint64_t cached = ~0ull;
+                                float z[4];
+                                for (int kk = 0; kk < 16; ++kk) {
+                                    uint64_t lin = lin0 + (uint64_t)kk;
+                                    if ((lin >> 2) != cached) { cached = lin >> 2; rsvd_normal4(p.seed, cached, z); }
+                                    uint32_t sel = (uint32_t)lin & 3u;
+                                    float f = sel == 0 ? z[0] : (sel == 1 ? z[1] : (sel == 2 ? z[2] : z[3]));
+                                    sts64(bbase + bswz(j, kk), (double)f);
+                                }
+                            }
+                        }
+                    } else if (p.ph_sc == 1 && ((p.ph_sk | (p.ph_off + n0)) & 3) == 0) {
+                        // linear index runs along the columns (left sketch of the ID): item = (k, column quad)
+                        constexpr int nitems = 16 * 2 * NB;    // 16 k  x  ncols/4 quads
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int item = tid + r * 128;
+                            if (item < nitems) {
+                                const int kk = item & 15, cq = item >> 4;
+                                const uint64_t lin = (uint64_t)(p.ph_off + ((i64)kc + kk) * p.ph_sk + n0 + 4 * cq);
+                                float z[4];
+                                rsvd_normal4(p.seed, lin >> 2, z);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) sts64(bbase + bswz(4 * cq + i, kk), (double)z[i]);
+                            }
+                        }
+                    } else {
+                        // arbitrary strides: one Philox block per element
+                        for (int e = tid; e < ncols * 16; e += 128) {
+                            const int kk = e & 15, j = e >> 4;
+                            const uint64_t lin = (uint64_t)(p.ph_off + ((i64)kc + kk) * p.ph_sk + (n0 + j) * p.ph_sc);
+                            sts64(bbase + bswz(j, kk), (double)rsvd_normal_at(p.seed, lin));
+                        }
+                    }
+                    mbar_arrive(full_bar(s));
+                }
+            }
+        }
+    } else {
+        // ===================== consumer warpgroups =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        const int cw = warp - 4;                  // rows [16*cw, 16*cw+16) of the tile, all columns
+        const int g = lane >> 2, t = lane & 3;
+        const int pg = (g >> 1) + 4 * (g & 1);    // physical row of logical row g in a K-major 8-row group
+
+        double acc[2][NB][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        // loop-invariant byte offsets inside a stage (s' = 0; s' = 1 adds 64 bytes before the XOR -> recomputed below)
+        const uint32_t b_row = (uint32_t)(pg * 128);
+        uint32_t b_ch[2], a_off[2][2];
+#pragma unroll
+        for (int sp = 0; sp < 2; ++sp) {
+            b_ch[sp] = (uint32_t)(((t + 4 * sp) ^ pg) << 4);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (A_KMAJOR) a_off[sp][c] = (uint32_t)((cw * 16 + c * 8 + pg) * 128) + b_ch[sp];      // c = row-block here
+                else { const int kk = 2 * t + c + 8 * sp; a_off[sp][c] = (uint32_t)(cw * 2048 + kk * 128 + ((g ^ (kk & 7)) << 4)); }
+            }
+        }
+
+        for (int it = 0; it < niter; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            mbar_wait(full_bar(s), ph);
+            const uint32_t a_base = sA + s * A_STAGE_BYTES;
+            const uint32_t b_base = sB + s * B_STAGE_BYTES + b_row;
+#pragma unroll
+            for (int sp = 0; sp < 2; ++sp) {
+                // a[x][c]: x = row-block (0/1), c = k-step within the pair
+                double a[2][2];
+                if (A_KMAJOR) {
+                    lds128(a_base + a_off[sp][0], a[0][0], a[0][1]);
+                    lds128(a_base + a_off[sp][1], a[1][0], a[1][1]);
+                } else {
+                    lds128(a_base + a_off[sp][0], a[0][0], a[1][0]);   // k-step c=0: rows 2g (block 0), 2g+1 (block 1)
+                    lds128(a_base + a_off[sp][1], a[0][1], a[1][1]);   // k-step c=1
+                }
+                // B fragments in chunks of 4 column groups, double-buffered so the LDS of chunk ch+1 are in flight
+                // while the DMMAs of chunk ch issue
+                constexpr int NCH = (NB + 3) / 4;
+                double b[2][4][2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < NB) lds128(b_base + (uint32_t)(i * 1024) + b_ch[sp], b[0][i][0], b[0][i][1]);
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (ch + 1 < NCH) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if ((ch + 1) * 4 + i < NB)
+                                lds128(b_base + (uint32_t)(((ch + 1) * 4 + i) * 1024) + b_ch[sp], b[(ch + 1) & 1][i][0], b[(ch + 1) & 1][i][1]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (ch * 4 + i < NB) {
+                                dmma(acc[0][ch * 4 + i][0], acc[0][ch * 4 + i][1], a[0][c], b[ch & 1][i][c]);
+                                dmma(acc[1][ch * 4 + i][0], acc[1][ch * 4 + i][1], a[1][c], b[ch & 1][i][c]);
+                            }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar(s));
+        }
+
+        // ---- epilogue: accumulators -> C, or the unit's partial tile ----
+        // accumulator acc[x][nb][cc]: row = 16*cw + (M-major: 2g + x | K-major: 8x + pg), col = 8*nb + t + 4*cc
+        if (nsplit > 1) {
+            double *P = p.part + (i64)blockIdx.x * PART_TILE;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int col = nb * 8 + t + 4 * cc;
+                        if (A_KMAJOR) {
+                            P[col * BM + cw * 16 + pg] = acc[0][nb][cc];
+                            P[col * BM + cw * 16 + 8 + pg] = acc[1][nb][cc];
+                        } else {
+                            *reinterpret_cast<double2 *>(P + col * BM + cw * 16 + 2 * g) = make_double2(acc[0][nb][cc], acc[1][nb][cc]);
+                        }
+                    }
+        } else {
+            const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const i64 col = n0 + nb * 8 + t + 4 * cc;
+                        if (col >= p.n) continue;
+                        double *cp = p.C + col * p.ldc;
+                        if (A_KMAJOR) {
+#pragma unroll
+                            for (int x = 0; x < 2; ++x) {
+                                const i64 row = m0 + cw * 16 + 8 * x + pg;
+                                if (row < p.m) {
+                                    double v = alpha * acc[x][nb][cc];
+                                    if (beta != 0.0) v += beta * cp[row];
+                                    cp[row] = v;
+                                }
+                            }
+                        } else {
+                            const i64 row = m0 + cw * 16 + 2 * g;
+                            if (p.c_vec2 && row + 1 < p.m) {
+                                double2 v = make_double2(alpha * acc[0][nb][cc], alpha * acc[1][nb][cc]);
+                                double2 *dst = reinterpret_cast<double2 *>(cp + row);
+                                if (beta != 0.0) { double2 o = *dst; v.x += beta * o.x; v.y += beta * o.y; }
+                                *dst = v;
+                            } else {
+#pragma unroll
+                                for (int x = 0; x < 2; ++x)
+                                    if (row + x < p.m) {
+                                        double v = alpha * acc[x][nb][cc];
+                                        if (beta != 0.0) v += beta * cp[row + x];
+                                        cp[row + x] = v;
+                                    }
+                            }
+                        }
+                    }
+        }
+    }
+}
+
+// sums the partial tiles of split units in fixed order: C = alpha * sum_s P[s] + beta * C.  One CTA per split tile.
+static __global__ void __launch_bounds__(256) tile_reduce_kernel(TmaP p, int first_split_tile_is_main) {
+    // split tiles: if s_main > 1 all main tiles (index 0..main_tiles-1) come first, then the tail tiles
+    int st = blockIdx.x, tile, nsplit, unit0;
+    const int n_main_split = (p.s_main > 1) ? p.main_tiles : 0;
+    if (st < n_main_split) { tile = st; nsplit = p.s_main; unit0 = tile * p.s_main; }
+    else { int tt = st - n_main_split; tile = p.main_tiles + tt; nsplit = p.s_tail; unit0 = p.main_tiles * p.s_main + tt * p.s_tail; }
+    (void)first_split_tile_is_main;
+    const int tile_n = tile % p.tiles_n, tile_m = tile / p.tiles_n;
+    const i64 m0 = (i64)tile_m * BM, n0 = (i64)tile_n * (8 * p.nb_tile);
+    const int ncols = (int)min((i64)(8 * p.nb_tile), p.n - n0);
+    const double *P = p.part + (i64)unit0 * PART_TILE;
+    for (int e = threadIdx.x; e < ncols * BM; e += blockDim.x) {
+        const int r = e % BM, c = e / BM;
+        const i64 row = m0 + r, col = n0 + c;
+        if (row >= p.m) continue;
+        double s = 0.0;
+        for (int u = 0; u < nsplit; ++u) s += P[(i64)u * PART_TILE + c * BM + r];
+        double *dst = p.C + col * p.ldc + row;
+        double v = p.alpha * s;
+        if (p.beta != 0.0) v += p.beta * (*dst);
+        *dst = v;
+    }
+}
+
+
+// one translation unit per NB instantiates this (gemm_tma_nb*.cu) so the variants compile in parallel
+template <int NB>
+bool launch_tma(bool a_kmajor, bool philox, const CUtensorMap &ma, const CUtensorMap &mb, const TmaP &p, unsigned grid) {
+    auto go = [&](auto kern) -> bool {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        kern<<<grid, NTHREADS, SMEM_BYTES, ctx().stream>>>(ma, mb, p);
+        count_launch();
+        return cudaGetLastError() == cudaSuccess;
+    };
+    if (a_kmajor) return philox ? go(gemm_tma_kernel<true, true, NB>) : go(gemm_tma_kernel<true, false, NB>);
+    return philox ? go(gemm_tma_kernel<false, true, NB>) : go(gemm_tma_kernel<false, false, NB>);
+}
+
+}  // namespace tma
+}  // namespace rsvd

@@ -11,10 +11,18 @@
 
 typedef RSVD_INT idx_t;
 
-/* ---- allocation: large matrices live in pinned memory so uploads run at PCIe speed -------------------------------- */
+/* ---- allocation: large matrices live in pinned memory so uploads/downloads run at PCIe speed.  Pinning costs
+ * ~0.5 ms/MB, so released pinned blocks are kept in a small cache (<= 1 GiB) and reused by later matrix_new calls
+ * (repeated API calls then allocate their U/V outputs for free). ---------------------------------------------------- */
 #define PINNED_MAX 256
 static void *g_pinned[PINNED_MAX];
+static size_t g_pinned_bytes[PINNED_MAX];
 static int g_npinned = 0;
+#define CACHE_MAX 16
+static void *g_cache[CACHE_MAX];
+static size_t g_cache_bytes[CACHE_MAX];
+static int g_ncache = 0;
+static size_t g_cache_total = 0;
 static size_t pinned_threshold(void) {
     static long thr = -2;
     if (thr == -2) {
@@ -26,16 +34,32 @@ static size_t pinned_threshold(void) {
 double *rsvd_host_calloc(size_t n) {
     size_t bytes = n * sizeof(double);
     if (bytes >= pinned_threshold() && g_npinned < PINNED_MAX && rsvd_b200_device_count() > 0) {
-        void *p = rsvd_b200_host_alloc(bytes);
-        if (p) { g_pinned[g_npinned++] = p; return (double *)p; }
+        void *p = NULL;
+        for (int i = 0; i < g_ncache; ++i)
+            if (g_cache_bytes[i] >= bytes && g_cache_bytes[i] <= bytes + (bytes >> 3)) {   /* reuse a cached block of ~the same size */
+                p = g_cache[i];
+                size_t cb = g_cache_bytes[i];
+                g_cache_total -= cb;
+                g_cache[i] = g_cache[g_ncache - 1]; g_cache_bytes[i] = g_cache_bytes[g_ncache - 1]; --g_ncache;
+                memset(p, 0, bytes);
+                g_pinned[g_npinned] = p; g_pinned_bytes[g_npinned++] = cb;
+                return (double *)p;
+            }
+        p = rsvd_b200_host_alloc(bytes);
+        if (p) { g_pinned[g_npinned] = p; g_pinned_bytes[g_npinned++] = bytes; return (double *)p; }
     }
     return (double *)calloc(n ? n : 1, sizeof(double));
 }
 void rsvd_host_free(double *p) {
     for (int i = 0; i < g_npinned; ++i)
         if (g_pinned[i] == (void *)p) {
-            g_pinned[i] = g_pinned[--g_npinned];
-            rsvd_b200_host_free(p);
+            size_t bytes = g_pinned_bytes[i];
+            g_pinned[i] = g_pinned[g_npinned - 1]; g_pinned_bytes[i] = g_pinned_bytes[g_npinned - 1]; --g_npinned;
+            if (g_ncache < CACHE_MAX && g_cache_total + bytes <= ((size_t)1 << 30)) {
+                g_cache[g_ncache] = p; g_cache_bytes[g_ncache++] = bytes; g_cache_total += bytes;
+            } else {
+                rsvd_b200_host_free(p);
+            }
             return;
         }
     free(p);
