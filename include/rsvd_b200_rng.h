@@ -70,9 +70,10 @@ RSVD_HD float rsvd_logf(float x) {
     int32_t ix = RSVD_F2I(x);
     int32_t e = ((ix >> 23) & 0xff) - 126;
     float m = RSVD_I2F((ix & 0x007fffff) | 0x3f000000); /* [0.5,1) */
-    float f;
-    if (m < 0.70710678118654752440f) { e -= 1; f = RSVD_FMA(m, 2.0f, -1.0f); }
-    else                              { f = RSVD_FMA(m, 1.0f, -1.0f); }
+    /* branch-free (selects only): data-dependent branches would diverge inside the GEMM's producer warps */
+    const int lt = m < 0.70710678118654752440f;
+    e -= lt;
+    float f = RSVD_FMA(m, lt ? 2.0f : 1.0f, -1.0f);
     float z = RSVD_FMA(f, f, 0.0f);
     float y = 7.0376836292E-2f;
     y = RSVD_FMA(y, f, -1.1514610310E-1f);
@@ -97,7 +98,8 @@ RSVD_HD float rsvd_logf(float x) {
 RSVD_HD void rsvd_sincos2pi(uint32_t t24, float *cs, float *sn) {
     uint32_t o = t24 >> 21;                                  /* octant 0..7 */
     float f = (float)(t24 & 0x1fffffu) * (1.0f / 2097152.0f); /* [0,1), exact */
-    if (o & 1u) f = RSVD_FMA(f, -1.0f, 1.0f);                /* exact */
+    const int odd = (int)(o & 1u);
+    f = odd ? RSVD_FMA(f, -1.0f, 1.0f) : f;                  /* exact */
     float a = RSVD_FMA(f, 0.78539816339744830962f, 0.0f);    /* [0, pi/4] */
     float z = RSVD_FMA(a, a, 0.0f);
     float ps = -1.9515295891E-4f;
@@ -112,13 +114,13 @@ RSVD_HD void rsvd_sincos2pi(uint32_t t24, float *cs, float *sn) {
     float c = RSVD_FMA(-0.5f, z, 1.0f);
     c = RSVD_FMA(pc, zz, c);
     /* theta = q*pi/2 +/- a  (+ for even octant, - for odd) */
-    uint32_t q = ((o + 1u) >> 1) & 3u;
-    float ss = (o & 1u) ? -s : s;
-    float sv, cv;
-    if (q == 0u)      { sv = ss;  cv = c;   }
-    else if (q == 1u) { sv = c;   cv = -ss; }
-    else if (q == 2u) { sv = -ss; cv = -c;  }
-    else              { sv = -c;  cv = ss;  }
+    const uint32_t q = ((o + 1u) >> 1) & 3u;
+    const float ss = odd ? -s : s;
+    /* q: 0 -> (ss, c), 1 -> (c, -ss), 2 -> (-ss, -c), 3 -> (-c, ss)  as (sin, cos); selects only */
+    const float sa = (q & 1u) ? c : ss;          /* |sin| source */
+    const float ca = (q & 1u) ? ss : c;          /* |cos| source */
+    const float sv = (q & 2u) ? -sa : sa;        /* sin is negated in quadrants 2, 3 */
+    const float cv = (q == 1u || q == 2u) ? -ca : ca;   /* cos is negated in quadrants 1, 2 */
     *cs = cv; *sn = sv;
 }
 

@@ -123,7 +123,7 @@ bool gemm_tma_try(const Gemm &g) {
         p.s_main = max(1, min(s, max_split));
     } else {
         const int rem = (int)(tiles % sms);
-        if (rem != 0 && rem * 4 < sms * 3 && max_split >= 2) {
+        if (rem != 0 && rem * 2 <= sms && max_split >= 2) {
             // only the last partial wave is split: `rem` tiles -> rem * s_tail units ~ one full wave of short units
             p.main_tiles = (int)(tiles - rem);
             p.s_tail = max(2, min(sms / rem, min(8, max_split)));

@@ -11,7 +11,8 @@ constexpr int STAGES = 5;
 constexpr int A_STAGE_BYTES = BM * BK * 8;       // 16 KB
 constexpr int B_STAGE_BYTES = BN_MAX * BK * 8;   // 16 KB
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 384;           // 1 producer + 2 consumer warpgroups
+constexpr int NTHREADS_PHILOX = 512;    // sketch mode: 2 producer warpgroups (alternate stages) + 2 consumer warpgroups
 constexpr int PART_TILE = BM * BN_MAX;           // doubles per partial tile
 
 struct TmaP {
@@ -82,7 +83,7 @@ __device__ __forceinline__ void decode_unit(const TmaP &p, int unit, int &tile, 
 
 // A_KMAJOR: op(A) = A^T with A stored k x m (TN); otherwise A stored m x k (NN).  PHILOX: B generated on the fly.
 template <bool A_KMAJOR, bool PHILOX, int NB>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(PHILOX ? NTHREADS_PHILOX : NTHREADS, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TmaP p) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -114,16 +115,22 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     __syncthreads();
 
-    if (warp < 4) {
-        // ===================== producer warpgroup =====================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    constexpr int NPWG = PHILOX ? 2 : 1;     // producer warpgroups
+    if (warp < 4 * NPWG) {
+        // ===================== producer warpgroup(s) =====================
+        // sketch mode: generating one Omega tile costs ~1.3x the DMMA time of a stage for a single warpgroup (latency-
+        // bound Philox + Box-Muller chains), so two warpgroups take alternate stages.
+        if (PHILOX) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        const int pw = warp >> 2;                // which producer warpgroup
+        const int ptid = tid & 127;              // thread index inside it
         if (PHILOX || tid == 0) {
-            for (int it = 0; it < niter; ++it) {
+            for (int it = pw; it < niter; it += NPWG) {
                 const int s = it % STAGES;
                 const uint32_t ph = (uint32_t)((it / STAGES) & 1);
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 const int kc = (it0 + it) * BK;
-                if (tid == 0) {
+                if (ptid == 0) {
                     const uint32_t fb = full_bar(s);
                     mbar_expect_tx(fb, PHILOX ? A_STAGE_BYTES : (A_STAGE_BYTES + b_bytes));
                     if (A_KMAJOR) {
@@ -142,7 +149,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     constexpr int ncols = 8 * NB;
                     if (p.ph_sk == 1) {
                         // linear index runs along k: thread = column, its 16 entries are 4 aligned Philox blocks
-                        const int j = tid;
+                        const int j = ptid;
                         if (j < ncols) {
                             const uint64_t lin0 = (uint64_t)(p.ph_off + (i64)kc + (n0 + j) * p.ph_sc);
                             if ((lin0 & 3u) == 0) {
@@ -171,7 +178,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         constexpr int nitems = 16 * 2 * NB;    // 16 k  x  ncols/4 quads
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
-                            const int item = tid + r * 128;
+                            const int item = ptid + r * 128;
                             if (item < nitems) {
                                 const int kk = item & 15, cq = item >> 4;
                                 const uint64_t lin = (uint64_t)(p.ph_off + ((i64)kc + kk) * p.ph_sk + n0 + 4 * cq);
@@ -183,7 +190,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         }
                     } else {
                         // arbitrary strides: one Philox block per element
-                        for (int e = tid; e < ncols * 16; e += 128) {
+                        for (int e = ptid; e < ncols * 16; e += 128) {
                             const int kk = e & 15, j = e >> 4;
                             const uint64_t lin = (uint64_t)(p.ph_off + ((i64)kc + kk) * p.ph_sk + (n0 + j) * p.ph_sc);
                             sts64(bbase + bswz(j, kk), (double)rsvd_normal_at(p.seed, lin));
@@ -195,8 +202,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
     } else {
         // ===================== consumer warpgroups =====================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-        const int cw = warp - 4;                  // rows [16*cw, 16*cw+16) of the tile, all columns
+        if (PHILOX) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        const int cw = warp - 4 * NPWG;           // rows [16*cw, 16*cw+16) of the tile, all columns
         const int g = lane >> 2, t = lane & 3;
         const int pg = (g >> 1) + 4 * (g & 1);    // physical row of logical row g in a K-major 8-row group
 
@@ -354,7 +362,7 @@ bool launch_tma(bool a_kmajor, bool philox, const CUtensorMap &ma, const CUtenso
     auto go = [&](auto kern) -> bool {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) { (void)cudaGetLastError(); return false; }
-        kern<<<grid, NTHREADS, SMEM_BYTES, ctx().stream>>>(ma, mb, p);
+        kern<<<grid, philox ? NTHREADS_PHILOX : NTHREADS, SMEM_BYTES, ctx().stream>>>(ma, mb, p);
         count_launch();
         return cudaGetLastError() == cudaSuccess;
     };
