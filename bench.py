@@ -226,10 +226,11 @@ def main():
 
     for _ in range(warmup):
         step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()       # before the barrier: spawning a child of a CUDA process can take 100s of ms
+        time.sleep(0.3)
+    barrier()
     launches0 = lib.rsvd_b200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(st):
