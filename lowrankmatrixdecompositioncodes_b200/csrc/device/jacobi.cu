@@ -79,6 +79,98 @@ __global__ void __launch_bounds__(JT) jacobi_step_kernel(double *G, i64 ldg, dou
     }
 }
 
+// ---- block version: one CTA owns two blocks of JB columns (2*JB = 16 columns staged in shared memory) and performs a
+// full inner sweep over their 120 pairs (15 rounds of 8 disjoint pairs, one warp per pair) before the next global step.
+// A sweep is then nblocks-1 global steps instead of n-1 (n = 520: 65 instead of 519), and the rotations of a step are
+// replayed on the 16 matching columns of V row by row from registers.
+constexpr int JB = 8;
+constexpr int JC = 2 * JB;
+constexpr int JROUNDS = JC - 1;
+constexpr int JPAIRS = JC / 2;
+
+__device__ __forceinline__ void local_pair(int round, int i, int &a, int &b) {
+    if (i == 0) { a = JC - 1; b = round; }
+    else { a = (round + i) % (JC - 1); b = (round - i + (JC - 1)) % (JC - 1); }
+}
+
+__global__ void __launch_bounds__(32 * JPAIRS) jacobi_block_step_kernel(double *G, i64 ldg, double *V, i64 ldv, int n, int nblk,
+                                                                        int r, double tol, int *rotated) {
+    extern __shared__ double sm[];
+    double *Gs = sm;                               // [JC][n]
+    double2 *rot = reinterpret_cast<double2 *>(sm + (size_t)JC * n);   // [JROUNDS][JPAIRS] (cs, sn)
+    __shared__ int any_rot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // block pair of this CTA (round-robin over nblk blocks)
+    const int i = blockIdx.x;
+    int P, Q;
+    if (i == 0) { P = nblk - 1; Q = r; }
+    else { P = (r + i) % (nblk - 1); Q = (r - i + (nblk - 1)) % (nblk - 1); }
+    if (P > Q) { int t = P; P = Q; Q = t; }
+    if (tid == 0) any_rot = 0;
+    // global column of local column c
+    auto gcol = [&](int c) { return (c < JB ? P * JB + c : Q * JB + (c - JB)); };
+    for (int c = 0; c < JC; ++c) {
+        const int col = gcol(c);
+        for (int row = tid; row < n; row += blockDim.x) Gs[(size_t)c * n + row] = (col < n) ? G[(i64)col * ldg + row] : 0.0;
+    }
+    __syncthreads();
+    for (int round = 0; round < JROUNDS; ++round) {
+        int a, b;
+        local_pair(round, warp, a, b);
+        double *ga = Gs + (size_t)a * n, *gb = Gs + (size_t)b * n;
+        double al = 0.0, be = 0.0, ga_gb = 0.0;
+        for (int row = lane; row < n; row += 32) {
+            const double x = ga[row], y = gb[row];
+            al = fma(x, x, al); be = fma(y, y, be); ga_gb = fma(x, y, ga_gb);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            al += __shfl_xor_sync(0xffffffffu, al, o);
+            be += __shfl_xor_sync(0xffffffffu, be, o);
+            ga_gb += __shfl_xor_sync(0xffffffffu, ga_gb, o);
+        }
+        double cs = 1.0, sn = 0.0;
+        if (fabs(ga_gb) > tol * sqrt(al * be) && al != 0.0 && be != 0.0) {
+            const double zeta = (be - al) / (2.0 * ga_gb);
+            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            cs = 1.0 / sqrt(1.0 + t * t); sn = cs * t;
+            for (int row = lane; row < n; row += 32) {
+                const double x = ga[row], y = gb[row];
+                ga[row] = cs * x - sn * y;
+                gb[row] = sn * x + cs * y;
+            }
+            if (lane == 0) any_rot = 1;
+        }
+        if (lane == 0) rot[round * JPAIRS + warp] = make_double2(cs, sn);
+        __syncthreads();
+    }
+    if (!any_rot) return;     // nothing changed: G and V stay as they are
+    if (tid == 0) *rotated = 1;
+    for (int c = 0; c < JC; ++c) {
+        const int col = gcol(c);
+        if (col < n)
+            for (int row = tid; row < n; row += blockDim.x) G[(i64)col * ldg + row] = Gs[(size_t)c * n + row];
+    }
+    // replay the rotations on the matching columns of V, one row per thread, all 16 values in registers
+    for (int row = tid; row < n; row += blockDim.x) {
+        double v[JC];
+#pragma unroll
+        for (int c = 0; c < JC; ++c) { const int col = gcol(c); v[c] = (col < n) ? V[(i64)col * ldv + row] : 0.0; }
+#pragma unroll
+        for (int round = 0; round < JROUNDS; ++round)
+#pragma unroll
+            for (int pi = 0; pi < JPAIRS; ++pi) {
+                int a, b;
+                local_pair(round, pi, a, b);
+                const double2 cssn = rot[round * JPAIRS + pi];
+                const double x = v[a], y = v[b];
+                v[a] = cssn.x * x - cssn.y * y;
+                v[b] = cssn.y * x + cssn.x * y;
+            }
+#pragma unroll
+        for (int c = 0; c < JC; ++c) { const int col = gcol(c); if (col < n) V[(i64)col * ldv + row] = v[c]; }
+    }
+}
+
 // sigma[j] = ||G(:,j)||, one warp per column
 __global__ void colnorm_kernel(const double *G, i64 ldg, int n, double *sigma) {
     const int lane = threadIdx.x & 31;
@@ -108,17 +200,29 @@ __global__ void finalize_kernel(const double *G, i64 ldg, const double *V, i64 l
 int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
     Ctx &c = ctx();
     set_identity(V, ldv, n);
-    const int N = (n + 1) & ~1;
     if (n > JT * JR) { set_error("rsvd_b200: Jacobi kernel supports n <= %d (got %d)", JT * JR, n); return -1; }
     if (n < 2) return 0;
     const double tol = 2.220446049250313e-16 * sqrt((double)n);
     int *flag = c.d_flag + 16;
-    // capture one sweep (N-1 dependent launches) in a graph
+    const int nblk = (((n + JB - 1) / JB) + 1) & ~1;      // even number of column blocks (the last may be padding)
+    const size_t smem = (size_t)JC * n * sizeof(double) + (size_t)JROUNDS * JPAIRS * sizeof(double2);
+    const bool use_block = nblk >= 4 && smem <= 200 * 1024;
+    if (use_block) RSVD_CUDA(cudaFuncSetAttribute(jacobi_block_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int N = (n + 1) & ~1;
+    // capture one sweep (dependent launches) in a graph
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
+    int launches_per_sweep = 0;
     RSVD_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
-    for (int r = 0; r < N - 1; ++r)
-        jacobi_step_kernel<<<N / 2, JT, 0, c.stream>>>(G, ldg, V, ldv, n, N, r, tol, flag);
+    if (use_block) {
+        for (int r = 0; r < nblk - 1; ++r)
+            jacobi_block_step_kernel<<<nblk / 2, 32 * JPAIRS, smem, c.stream>>>(G, ldg, V, ldv, n, nblk, r, tol, flag);
+        launches_per_sweep = nblk - 1;
+    } else {
+        for (int r = 0; r < N - 1; ++r)
+            jacobi_step_kernel<<<N / 2, JT, 0, c.stream>>>(G, ldg, V, ldv, n, N, r, tol, flag);
+        launches_per_sweep = N - 1;
+    }
     RSVD_CUDA(cudaStreamEndCapture(c.stream, &graph));
     RSVD_CUDA(cudaGraphInstantiate(&exec, graph, 0));
     int sweeps = 0;
@@ -127,7 +231,7 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
         for (; sweeps < max_sweeps; ++sweeps) {
             RSVD_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), c.stream));
             RSVD_CUDA(cudaGraphLaunch(exec, c.stream));
-            count_launch(N - 1);
+            count_launch(launches_per_sweep);
             RSVD_CUDA(cudaMemcpyAsync(c.h_flag + 16, flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
             RSVD_CUDA(cudaStreamSynchronize(c.stream));
             if (c.h_flag[16] == 0) { ++sweeps; break; }
@@ -135,7 +239,7 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
         cudaGraphExecDestroy(exec);
     }
     if (graph) cudaGraphDestroy(graph);
-    if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d\n", n, sweeps);
+    if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d (%s)\n", n, sweeps, use_block ? "block" : "vector");
     return sweeps;
 }
 

@@ -215,3 +215,26 @@ def test_evaluation_helpers_print_reference_metric(api, capfd):
     P = np.zeros_like(A)
     P[:, idx] = np.hstack([A[:, idx[:20]], A[:, idx[:20]] @ T])
     assert api.lib.rsvd_b200_api_last_percent_error() == pytest.approx(O.get_percent_error_between_two_mats(A, P), rel=1e-9)
+
+
+def test_relinked_reference_driver_runs_end_to_end(tmp_path, oracle):
+    """The reference's own driver_multi_core_mkl1.c, compiled UNMODIFIED against include/ and linked with the B200 libraries
+    (oracle/build_ref.sh), loads ../../matrix_data/A_mat_1kx2k.bin and prints the percent error of a k=200,p=10,q=2 SVD."""
+    import os
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "relink", "driver_multi_core_mkl1")
+    if not os.path.exists(exe):
+        pytest.skip("relinked driver not built")
+    A, _ = O.make_matrix(1000, 2000, "logspace", seed=7)
+    (tmp_path / "matrix_data").mkdir()
+    O.write_matrix_binary(A, str(tmp_path / "matrix_data" / "A_mat_1kx2k.bin"), 32)
+    cwd = tmp_path / "x" / "y"
+    cwd.mkdir(parents=True)
+    out = subprocess.run([os.path.abspath(exe)], cwd=str(cwd), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    m = re.search(r"percent_error between M and U S V\^T = ([0-9.eE+-]+)", out.stdout)
+    assert m, out.stdout
+    Ur, Sr, Vr = oracle.svd_rand(A, 200, 10, 1, 2, 1, seed=777)
+    assert float(m.group(1)) == pytest.approx(100 * recon_err(A, Ur, Sr, Vr), rel=1e-4)
+    assert "normM = %f" % np.linalg.norm(A) in out.stdout
