@@ -93,6 +93,8 @@ __device__ __forceinline__ void local_pair(int round, int i, int &a, int &b) {
     else { a = (round + i) % (JC - 1); b = (round - i + (JC - 1)) % (JC - 1); }
 }
 
+// RPL = rows per lane (n <= 32*RPL): the two columns of a pair live in registers between the dot products and the rotation
+template <int RPL>
 __global__ void __launch_bounds__(32 * JPAIRS) jacobi_block_step_kernel(double *G, i64 ldg, double *V, i64 ldv, int n, int nblk,
                                                                         int r, double tol, int *rotated) {
     extern __shared__ double sm[];
@@ -118,25 +120,37 @@ __global__ void __launch_bounds__(32 * JPAIRS) jacobi_block_step_kernel(double *
         int a, b;
         local_pair(round, warp, a, b);
         double *ga = Gs + (size_t)a * n, *gb = Gs + (size_t)b * n;
-        double al = 0.0, be = 0.0, ga_gb = 0.0;
-        for (int row = lane; row < n; row += 32) {
-            const double x = ga[row], y = gb[row];
-            al = fma(x, x, al); be = fma(y, y, be); ga_gb = fma(x, y, ga_gb);
+        double x[RPL], y[RPL];
+        double al0 = 0.0, be0 = 0.0, gm0 = 0.0, al1 = 0.0, be1 = 0.0, gm1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            const int row = lane + 32 * k;
+            x[k] = row < n ? ga[row] : 0.0;
+            y[k] = row < n ? gb[row] : 0.0;
         }
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            if (k & 1) { al1 = fma(x[k], x[k], al1); be1 = fma(y[k], y[k], be1); gm1 = fma(x[k], y[k], gm1); }
+            else       { al0 = fma(x[k], x[k], al0); be0 = fma(y[k], y[k], be0); gm0 = fma(x[k], y[k], gm0); }
+        }
+        double al = al0 + al1, be = be0 + be1, gm = gm0 + gm1;
         for (int o = 16; o > 0; o >>= 1) {
             al += __shfl_xor_sync(0xffffffffu, al, o);
             be += __shfl_xor_sync(0xffffffffu, be, o);
-            ga_gb += __shfl_xor_sync(0xffffffffu, ga_gb, o);
+            gm += __shfl_xor_sync(0xffffffffu, gm, o);
         }
         double cs = 1.0, sn = 0.0;
-        if (fabs(ga_gb) > tol * sqrt(al * be) && al != 0.0 && be != 0.0) {
-            const double zeta = (be - al) / (2.0 * ga_gb);
+        if (fabs(gm) > tol * sqrt(al * be) && al != 0.0 && be != 0.0) {
+            const double zeta = (be - al) / (2.0 * gm);
             const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            cs = 1.0 / sqrt(1.0 + t * t); sn = cs * t;
-            for (int row = lane; row < n; row += 32) {
-                const double x = ga[row], y = gb[row];
-                ga[row] = cs * x - sn * y;
-                gb[row] = sn * x + cs * y;
+            cs = rsqrt(1.0 + t * t); sn = cs * t;
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                const int row = lane + 32 * k;
+                if (row < n) {
+                    ga[row] = cs * x[k] - sn * y[k];
+                    gb[row] = sn * x[k] + cs * y[k];
+                }
             }
             if (lane == 0) any_rot = 1;
         }
@@ -162,9 +176,9 @@ __global__ void __launch_bounds__(32 * JPAIRS) jacobi_block_step_kernel(double *
                 int a, b;
                 local_pair(round, pi, a, b);
                 const double2 cssn = rot[round * JPAIRS + pi];
-                const double x = v[a], y = v[b];
-                v[a] = cssn.x * x - cssn.y * y;
-                v[b] = cssn.y * x + cssn.x * y;
+                const double xv = v[a], yv = v[b];
+                v[a] = cssn.x * xv - cssn.y * yv;
+                v[b] = cssn.y * xv + cssn.x * yv;
             }
 #pragma unroll
         for (int c = 0; c < JC; ++c) { const int col = gcol(c); if (col < n) V[(i64)col * ldv + row] = v[c]; }
@@ -206,8 +220,10 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
     int *flag = c.d_flag + 16;
     const int nblk = (((n + JB - 1) / JB) + 1) & ~1;      // even number of column blocks (the last may be padding)
     const size_t smem = (size_t)JC * n * sizeof(double) + (size_t)JROUNDS * JPAIRS * sizeof(double2);
-    const bool use_block = nblk >= 4 && smem <= 200 * 1024;
-    if (use_block) RSVD_CUDA(cudaFuncSetAttribute(jacobi_block_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool use_block = nblk >= 4 && smem <= 200 * 1024 && !getenv("RSVD_B200_JACOBI_VECTOR");
+    typedef void (*BlockKern)(double *, i64, double *, i64, int, int, int, double, int *);
+    BlockKern bk = n <= 32 * 17 ? jacobi_block_step_kernel<17> : (n <= 32 * 33 ? jacobi_block_step_kernel<33> : jacobi_block_step_kernel<40>);
+    if (use_block) RSVD_CUDA(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int N = (n + 1) & ~1;
     // capture one sweep (dependent launches) in a graph
     cudaGraph_t graph = nullptr;
@@ -216,7 +232,7 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
     RSVD_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
     if (use_block) {
         for (int r = 0; r < nblk - 1; ++r)
-            jacobi_block_step_kernel<<<nblk / 2, 32 * JPAIRS, smem, c.stream>>>(G, ldg, V, ldv, n, nblk, r, tol, flag);
+            bk<<<nblk / 2, 32 * JPAIRS, smem, c.stream>>>(G, ldg, V, ldv, n, nblk, r, tol, flag);
         launches_per_sweep = nblk - 1;
     } else {
         for (int r = 0; r < N - 1; ++r)

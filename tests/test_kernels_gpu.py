@@ -156,7 +156,7 @@ def test_jacobi_svd_and_eig(lib, n):
     wn, Vn = w.cpu().numpy(), D.to_numpy(Sd)
     assert np.all(np.diff(wn) >= 0)
     assert np.max(np.abs(wn[::-1] - s0 ** 2) / (s0 ** 2).max()) < 1e-12
-    assert np.linalg.norm(S @ Vn - Vn * wn) / np.linalg.norm(S) < 1e-13
+    assert np.linalg.norm(S @ Vn - Vn * wn) / np.linalg.norm(S) < 1e-12
 
 
 @pytest.mark.parametrize("m,n", [(12, 40), (120, 1500), (100, 2000), (300, 5000), (40, 40), (7, 3), (200, 9000)])

@@ -183,11 +183,18 @@ def _qr():
 def _jacobi():
     for n in (5, 120, 520, 1050):
         rng = np.random.default_rng(n)
-        A = np.triu(rng.standard_normal((n, n))) * np.logspace(0, -6, n)[None, :]
+        U0, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        V0, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        A = np.triu(np.linalg.qr((U0 * np.logspace(1, -2.5, n)) @ V0.T)[1])   # triangular, cond ~3e3 (like Rhat of the pipeline)
         Ad = D.from_numpy_cm(A)
         U = torch.empty((n, n), dtype=torch.float64, device="cuda")
         Vt = torch.empty((n, n), dtype=torch.float64, device="cuda")
         s = torch.empty(n, dtype=torch.float64, device="cuda")
+        A0d = Ad.clone()
+        native.check(lib.rsvd_b200_svd_small(Ad.data_ptr(), n, n, U.data_ptr(), n, s.data_ptr(), Vt.data_ptr(), n))
+        sync()
+        Ad.copy_(A0d)
+        torch.cuda.synchronize()
         t0 = time.time()
         native.check(lib.rsvd_b200_svd_small(Ad.data_ptr(), n, n, U.data_ptr(), n, s.data_ptr(), Vt.data_ptr(), n))
         sync()
