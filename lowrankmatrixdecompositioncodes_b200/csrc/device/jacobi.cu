@@ -5,8 +5,11 @@
 //
 // One sweep = N-1 round-robin steps of N/2 disjoint column pairs; each pair is one CTA that keeps both columns in
 // registers, forms the 2x2 Gram entries with a block reduction and rotates the columns of G and of the
-// accumulated V.  The l x l working set (<= 2 x 8.8 MB at l = 1050) stays L2-resident.  A whole sweep is captured
-// once in a CUDA graph and replayed until a sweep applies no rotation.
+// accumulated V.  The l x l working set (<= 2 x 8.8 MB at l = 1050) stays L2-resident.
+// The whole iteration (all steps of all sweeps, convergence test included) is ONE persistent cooperative kernel: the
+// N/2 CTAs are co-resident and separate the steps with a device-wide barrier (an atomic counter in L2, ~1 us) instead
+// of one kernel launch per step (~4.3 us in a CUDA graph: 519 steps x 9 sweeps at l = 520).  A graph-replayed
+// per-step kernel remains as the fallback when the grid cannot be co-resident.
 #include "common.cuh"
 #include <algorithm>
 #include <vector>
@@ -79,109 +82,87 @@ __global__ void __launch_bounds__(JT) jacobi_step_kernel(double *G, i64 ldg, dou
     }
 }
 
-// ---- block version: one CTA owns two blocks of JB columns (2*JB = 16 columns staged in shared memory) and performs a
-// full inner sweep over their 120 pairs (15 rounds of 8 disjoint pairs, one warp per pair) before the next global step.
-// A sweep is then nblocks-1 global steps instead of n-1 (n = 520: 65 instead of 519), and the rotations of a step are
-// replayed on the 16 matching columns of V row by row from registers.
-constexpr int JB = 8;
-constexpr int JC = 2 * JB;
-constexpr int JROUNDS = JC - 1;
-constexpr int JPAIRS = JC / 2;
-
-__device__ __forceinline__ void local_pair(int round, int i, int &a, int &b) {
-    if (i == 0) { a = JC - 1; b = round; }
-    else { a = (round + i) % (JC - 1); b = (round - i + (JC - 1)) % (JC - 1); }
-}
-
-// RPL = rows per lane (n <= 32*RPL): the two columns of a pair live in registers between the dot products and the rotation
-template <int RPL>
-__global__ void __launch_bounds__(32 * JPAIRS) jacobi_block_step_kernel(double *G, i64 ldg, double *V, i64 ldv, int n, int nblk,
-                                                                        int r, double tol, int *rotated) {
-    extern __shared__ double sm[];
-    double *Gs = sm;                               // [JC][n]
-    double2 *rot = reinterpret_cast<double2 *>(sm + (size_t)JC * n);   // [JROUNDS][JPAIRS] (cs, sn)
-    __shared__ int any_rot;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // block pair of this CTA (round-robin over nblk blocks)
-    const int i = blockIdx.x;
-    int P, Q;
-    if (i == 0) { P = nblk - 1; Q = r; }
-    else { P = (r + i) % (nblk - 1); Q = (r - i + (nblk - 1)) % (nblk - 1); }
-    if (P > Q) { int t = P; P = Q; Q = t; }
-    if (tid == 0) any_rot = 0;
-    // global column of local column c
-    auto gcol = [&](int c) { return (c < JB ? P * JB + c : Q * JB + (c - JB)); };
-    for (int c = 0; c < JC; ++c) {
-        const int col = gcol(c);
-        for (int row = tid; row < n; row += blockDim.x) Gs[(size_t)c * n + row] = (col < n) ? G[(i64)col * ldg + row] : 0.0;
+// ---- persistent version -----------------------------------------------------------------------------------------
+// device-wide barrier: monotone counter, generation g completes when it reaches (g+1)*gridDim.x.  Bounded spin: a barrier
+// that cannot complete (grid not co-resident) sets *err and lets every CTA leave instead of hanging the GPU.
+__device__ __forceinline__ bool grid_barrier(int *bar, int gen, int *err) {
+    __syncthreads();
+    __shared__ int ok_s;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1);
+        const int target = (gen + 1) * (int)gridDim.x;
+        int ok = 1;
+        long long spins = 0;
+        while (*((volatile int *)bar) < target) {
+            if (++spins > (1ll << 26) || *((volatile int *)err)) { ok = 0; *err = 1; break; }
+        }
+        __threadfence();
+        ok_s = ok;
     }
     __syncthreads();
-    for (int round = 0; round < JROUNDS; ++round) {
-        int a, b;
-        local_pair(round, warp, a, b);
-        double *ga = Gs + (size_t)a * n, *gb = Gs + (size_t)b * n;
-        double x[RPL], y[RPL];
-        double al0 = 0.0, be0 = 0.0, gm0 = 0.0, al1 = 0.0, be1 = 0.0, gm1 = 0.0;
+    return ok_s != 0;
+}
+
+// ctl[0] = barrier counter, ctl[1] = error flag, ctl[2] = sweeps done, ctl[8 + s] = CTAs that rotated in sweep s
+__global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ldg, double *V, i64 ldv, int n, int N, double tol,
+                                                               int max_sweeps, int *ctl) {
+    __shared__ double sh[3 * (JT / 32)];
+    const int i = blockIdx.x;
+    int gen = 0;
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        int rotated = 0;
+        for (int r = 0; r < N - 1; ++r) {
+            int p, q;
+            if (i == 0) { p = N - 1; q = r; }
+            else { p = (r + i) % (N - 1); q = (r - i + (N - 1)) % (N - 1); }
+            if (p > q) { int t = p; p = q; q = t; }
+            if (q < n) {
+                double *gp = G + (i64)p * ldg, *gq = G + (i64)q * ldg;
+                double xp[JR], xq[JR];
+                double a = 0.0, b = 0.0, c = 0.0;
 #pragma unroll
-        for (int k = 0; k < RPL; ++k) {
-            const int row = lane + 32 * k;
-            x[k] = row < n ? ga[row] : 0.0;
-            y[k] = row < n ? gb[row] : 0.0;
-        }
+                for (int k = 0; k < JR; ++k) {
+                    int row = threadIdx.x + k * JT;
+                    xp[k] = row < n ? __ldcg(gp + row) : 0.0;     // L2 loads: other SMs wrote these columns in the previous step
+                    xq[k] = row < n ? __ldcg(gq + row) : 0.0;
+                    a = fma(xp[k], xp[k], a);
+                    b = fma(xq[k], xq[k], b);
+                    c = fma(xp[k], xq[k], c);
+                }
+                __syncthreads();     // sh reuse across steps
+                block_sum3(a, b, c, sh);
+                if (fabs(c) > tol * sqrt(a * b) && a != 0.0 && b != 0.0) {
+                    const double zeta = (b - a) / (2.0 * c);
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                    rotated = 1;
 #pragma unroll
-        for (int k = 0; k < RPL; ++k) {
-            if (k & 1) { al1 = fma(x[k], x[k], al1); be1 = fma(y[k], y[k], be1); gm1 = fma(x[k], y[k], gm1); }
-            else       { al0 = fma(x[k], x[k], al0); be0 = fma(y[k], y[k], be0); gm0 = fma(x[k], y[k], gm0); }
-        }
-        double al = al0 + al1, be = be0 + be1, gm = gm0 + gm1;
-        for (int o = 16; o > 0; o >>= 1) {
-            al += __shfl_xor_sync(0xffffffffu, al, o);
-            be += __shfl_xor_sync(0xffffffffu, be, o);
-            gm += __shfl_xor_sync(0xffffffffu, gm, o);
-        }
-        double cs = 1.0, sn = 0.0;
-        if (fabs(gm) > tol * sqrt(al * be) && al != 0.0 && be != 0.0) {
-            const double zeta = (be - al) / (2.0 * gm);
-            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            cs = rsqrt(1.0 + t * t); sn = cs * t;
+                    for (int k = 0; k < JR; ++k) {
+                        int row = threadIdx.x + k * JT;
+                        if (row < n) {
+                            gp[row] = cs * xp[k] - sn * xq[k];
+                            gq[row] = sn * xp[k] + cs * xq[k];
+                        }
+                    }
+                    double *vp = V + (i64)p * ldv, *vq = V + (i64)q * ldv;
 #pragma unroll
-            for (int k = 0; k < RPL; ++k) {
-                const int row = lane + 32 * k;
-                if (row < n) {
-                    ga[row] = cs * x[k] - sn * y[k];
-                    gb[row] = sn * x[k] + cs * y[k];
+                    for (int k = 0; k < JR; ++k) {
+                        int row = threadIdx.x + k * JT;
+                        if (row < n) {
+                            double y = __ldcg(vp + row), z = __ldcg(vq + row);
+                            vp[row] = cs * y - sn * z;
+                            vq[row] = sn * y + cs * z;
+                        }
+                    }
                 }
             }
-            if (lane == 0) any_rot = 1;
+            if (r == N - 2 && rotated && threadIdx.x == 0) atomicAdd(ctl + 8 + sweep, 1);
+            if (!grid_barrier(ctl, gen++, ctl + 1)) return;
         }
-        if (lane == 0) rot[round * JPAIRS + warp] = make_double2(cs, sn);
-        __syncthreads();
-    }
-    if (!any_rot) return;     // nothing changed: G and V stay as they are
-    if (tid == 0) *rotated = 1;
-    for (int c = 0; c < JC; ++c) {
-        const int col = gcol(c);
-        if (col < n)
-            for (int row = tid; row < n; row += blockDim.x) G[(i64)col * ldg + row] = Gs[(size_t)c * n + row];
-    }
-    // replay the rotations on the matching columns of V, one row per thread, all 16 values in registers
-    for (int row = tid; row < n; row += blockDim.x) {
-        double v[JC];
-#pragma unroll
-        for (int c = 0; c < JC; ++c) { const int col = gcol(c); v[c] = (col < n) ? V[(i64)col * ldv + row] : 0.0; }
-#pragma unroll
-        for (int round = 0; round < JROUNDS; ++round)
-#pragma unroll
-            for (int pi = 0; pi < JPAIRS; ++pi) {
-                int a, b;
-                local_pair(round, pi, a, b);
-                const double2 cssn = rot[round * JPAIRS + pi];
-                const double xv = v[a], yv = v[b];
-                v[a] = cssn.x * xv - cssn.y * yv;
-                v[b] = cssn.y * xv + cssn.x * yv;
-            }
-#pragma unroll
-        for (int c = 0; c < JC; ++c) { const int col = gcol(c); if (col < n) V[(i64)col * ldv + row] = v[c]; }
+        const int nrot = *((volatile int *)(ctl + 8 + sweep));
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl[2] = sweep + 1;
+        if (nrot == 0) break;
     }
 }
 
@@ -214,40 +195,53 @@ __global__ void finalize_kernel(const double *G, i64 ldg, const double *V, i64 l
 int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
     Ctx &c = ctx();
     set_identity(V, ldv, n);
+    const int N = (n + 1) & ~1;
     if (n > JT * JR) { set_error("rsvd_b200: Jacobi kernel supports n <= %d (got %d)", JT * JR, n); return -1; }
     if (n < 2) return 0;
     const double tol = 2.220446049250313e-16 * sqrt((double)n);
+    const int max_sweeps = 40;
+    int sweeps = 0;
+
+    // persistent path: all N/2 CTAs co-resident (cooperative launch guarantees it or fails cleanly)
+    static int coop = -1, blocks_per_sm = 0;
+    if (coop < 0) {
+        RSVD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
+        RSVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_persistent_kernel, JT, 0));
+    }
+    if (coop > 0 && N / 2 <= blocks_per_sm * c.sms && !getenv("RSVD_B200_JACOBI_GRAPH")) {
+        int *ctl = (int *)dalloc_bytes(64 * sizeof(int));
+        RSVD_CUDA(cudaMemsetAsync(ctl, 0, 64 * sizeof(int), c.stream));
+        int ms = max_sweeps;
+        void *args[] = {&G, &ldg, &V, &ldv, (void *)&n, (void *)&N, (void *)&tol, &ms, &ctl};
+        cudaError_t e = cudaLaunchCooperativeKernel((void *)jacobi_persistent_kernel, dim3(N / 2), dim3(JT), args, 0, c.stream);
+        if (e == cudaSuccess) {
+            count_launch();
+            RSVD_CUDA(cudaMemcpyAsync(c.h_flag + 16, ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+            RSVD_CUDA(cudaStreamSynchronize(c.stream));
+            dfree(ctl);
+            if (c.h_flag[17]) { set_error("rsvd_b200: Jacobi device-wide barrier timed out"); return -1; }
+            sweeps = c.h_flag[18];
+            if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d (persistent)\n", n, sweeps);
+            return sweeps;
+        }
+        (void)cudaGetLastError();
+        dfree(ctl);
+    }
+
+    // fallback: one kernel per step, a whole sweep replayed from a CUDA graph
     int *flag = c.d_flag + 16;
-    const int nblk = (((n + JB - 1) / JB) + 1) & ~1;      // even number of column blocks (the last may be padding)
-    const size_t smem = (size_t)JC * n * sizeof(double) + (size_t)JROUNDS * JPAIRS * sizeof(double2);
-    const bool use_block = nblk >= 4 && smem <= 200 * 1024 && !getenv("RSVD_B200_JACOBI_VECTOR");
-    typedef void (*BlockKern)(double *, i64, double *, i64, int, int, int, double, int *);
-    BlockKern bk = n <= 32 * 17 ? jacobi_block_step_kernel<17> : (n <= 32 * 33 ? jacobi_block_step_kernel<33> : jacobi_block_step_kernel<40>);
-    if (use_block) RSVD_CUDA(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int N = (n + 1) & ~1;
-    // capture one sweep (dependent launches) in a graph
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    int launches_per_sweep = 0;
     RSVD_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
-    if (use_block) {
-        for (int r = 0; r < nblk - 1; ++r)
-            bk<<<nblk / 2, 32 * JPAIRS, smem, c.stream>>>(G, ldg, V, ldv, n, nblk, r, tol, flag);
-        launches_per_sweep = nblk - 1;
-    } else {
-        for (int r = 0; r < N - 1; ++r)
-            jacobi_step_kernel<<<N / 2, JT, 0, c.stream>>>(G, ldg, V, ldv, n, N, r, tol, flag);
-        launches_per_sweep = N - 1;
-    }
+    for (int r = 0; r < N - 1; ++r)
+        jacobi_step_kernel<<<N / 2, JT, 0, c.stream>>>(G, ldg, V, ldv, n, N, r, tol, flag);
     RSVD_CUDA(cudaStreamEndCapture(c.stream, &graph));
     RSVD_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-    int sweeps = 0;
-    const int max_sweeps = 40;
     if (exec) {
         for (; sweeps < max_sweeps; ++sweeps) {
             RSVD_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), c.stream));
             RSVD_CUDA(cudaGraphLaunch(exec, c.stream));
-            count_launch(launches_per_sweep);
+            count_launch(N - 1);
             RSVD_CUDA(cudaMemcpyAsync(c.h_flag + 16, flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
             RSVD_CUDA(cudaStreamSynchronize(c.stream));
             if (c.h_flag[16] == 0) { ++sweeps; break; }
@@ -255,7 +249,7 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
         cudaGraphExecDestroy(exec);
     }
     if (graph) cudaGraphDestroy(graph);
-    if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d (%s)\n", n, sweeps, use_block ? "block" : "vector");
+    if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d (graph)\n", n, sweeps);
     return sweeps;
 }
 
