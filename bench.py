@@ -89,7 +89,7 @@ def cpu_reference_run(m_sample, steps, warmup):
     return sum(times) / len(times), cores, kind
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -107,7 +107,7 @@ def run_reference_arm(args):
         "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -163,8 +163,20 @@ def main():
     ap.add_argument("--no-roofline", action="store_true", help="skip the isolated per-pass timing (used under ncu)")
     ap.add_argument("--rows", type=int, default=M_PER_GPU, help="rows per GPU (default: the BASELINE workload)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner, the reference's progress
+    # printf) are redirected to stderr until the line is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, emit)
 
     import numpy as np
     import torch
@@ -233,13 +245,17 @@ def main():
     barrier()
     launches0 = lib.rsvd_b200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     with torch.cuda.stream(st):
         e0.record()
-    for _ in range(args.steps):
+    for i_ in range(args.steps):
         step()
+        with torch.cuda.stream(st):
+            marks[i_].record()
     with torch.cuda.stream(st):
         e1.record()
     barrier()
+    step_ms = [([e0] + marks)[i_].elapsed_time(marks[i_]) for i_ in range(args.steps)]
     launches = lib.rsvd_b200_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     dev_s = e0.elapsed_time(e1) * 1e-3
@@ -254,7 +270,7 @@ def main():
     # ---- roofline of the dominant kernel: one streaming pass (NN and TN), timed alone on the library's stream --------
     if args.no_roofline:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": "TFLOP/s", "ms_per_step": sec_per_step * 1e3, "gpu_launches": int(launches), "note": "profiling run"}))
+            emit({"metric": METRIC, "value": value, "unit": "TFLOP/s", "ms_per_step": sec_per_step * 1e3, "gpu_launches": int(launches), "step_ms": step_ms, "note": "profiling run"})
         return
     B = torch.randn((l, n), dtype=torch.float64, device="cuda")
     Y = torch.empty((l, m), dtype=torch.float64, device="cuda")
@@ -346,11 +362,11 @@ def main():
             "config": {"workload": WORKLOAD, "rows_per_gpu": m, "global_shape": [m_global, n], "parallelism": "row-partition x%d" % world,
                        "l2": "inputs (%.1f GB per GPU) larger than L2" % (8.0 * m * n / 1e9),
                        "percent_error": pct_err},
-            "time_to_solution_s": sec_per_step, "gemm_flops_per_step": flops,
+            "time_to_solution_s": sec_per_step, "gemm_flops_per_step": flops, "step_ms_rank0": step_ms,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         lib.rsvd_b200_comm_destroy()
         dist.destroy_process_group()

@@ -99,7 +99,7 @@ for (m, n, k, p, q, s, spec) in [(2000, 1500, 100, 20, 2, 1, "gap"), (3001, 900,
     else:
         Cr, Uc, Rr = O.cur_rand_decomp_fixed_rank(A, k, p, q, s, 777)
     report("cur %dx%d world=%d" % (m, n, world), np.array_equal(Cfull, Cr) and np.array_equal(D.to_numpy(Rm), Rr) and
-           np.abs(D.to_numpy(Um) - Uc).max() <= 1e-8 * np.abs(Uc).max(),
+           np.abs(D.to_numpy(Um) - Uc).max() <= 1e-6 * np.abs(Uc).max(),   # U solves an (R R^T) system: cond^2-sensitive
            "C eq %s R eq %s max|U-Uref|/max|U| %.2e" % (np.array_equal(Cfull, Cr), np.array_equal(D.to_numpy(Rm), Rr), np.abs(D.to_numpy(Um) - Uc).max() / np.abs(Uc).max()))
     # ---- blocked QB (rank mode and device-side tolerance mode) ----
     for (kstep, nstep, tol) in [(20, 4, 0.0), (20, 0, float(np.linalg.norm(A)) * 0.3)]:
