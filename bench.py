@@ -239,7 +239,7 @@ def main():
     for _ in range(warmup):
         step()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()       # before the barrier: spawning a child of a CUDA process can take 100s of ms
         time.sleep(0.3)
     barrier()

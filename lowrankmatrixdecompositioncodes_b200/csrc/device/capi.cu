@@ -27,6 +27,14 @@ using namespace rsvd;
         if (!ctx().inited) return 1; \
     } while (0)
 
+// Algorithm-level entry points return with their results complete (like the reference's synchronous API).  Besides the
+// simpler contract this keeps row-partitioned ranks in step: a rank whose host thread ran ahead into the next call while
+// its peer was still finishing the previous one produced sporadic 100-600 ms stalls at 2 GPUs.
+static int finish(int rc) {
+    RSVD_CUDA(cudaStreamSynchronize(ctx().stream));
+    return rc ? rc : g_status;
+}
+
 static i64 global_rows(i64 m_local) {
     // in a row partition the option "m_global" carries the total row count; default = local
     return (ctx().world > 1 && ctx().m_global > 0) ? (i64)ctx().m_global : m_local;
@@ -114,44 +122,44 @@ int rsvd_b200_svd_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda
                            int s, uint64_t seed, const double *omega, double *U, rsvd_i64 ldu, double *S, double *V,
                            rsvd_i64 ldv) {
     READY();
-    return svd_rand(A, m, n, lda, k, p, vnum, q, s, seed, omega, U, ldu, S, V, ldv);
+    return finish(svd_rand(A, m, n, lda, k, p, vnum, q, s, seed, omega, U, ldu, S, V, ldv));
 }
 
 int rsvd_b200_randqb_dev(double *Awork, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 kstep, rsvd_i64 nstep, double tol,
                          int q, int s, uint64_t seed, double *Q, rsvd_i64 ldq, double *B, rsvd_i64 ldb, rsvd_i64 *frank) {
     READY();
     // capacity of Q/B in columns/rows: ldb rows of B were allocated by the caller
-    return randqb(Awork, m, n, lda, kstep, nstep, tol, q, s, seed, Q, ldq, B, ldb, ldb, frank);
+    return finish(randqb(Awork, m, n, lda, kstep, nstep, tol, q, s, seed, Q, ldq, B, ldb, ldb, frank));
 }
 
 int rsvd_b200_svd_from_q_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, double *Q, rsvd_i64 ldq, rsvd_i64 l,
                              rsvd_i64 k, int vnum, double *U, rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv) {
     READY();
-    return svd_from_q(A, m, n, lda, Q, ldq, l, k, vnum, U, ldu, S, V, ldv);
+    return finish(svd_from_q(A, m, n, lda, Q, ldq, l, k, vnum, U, ldu, S, V, ldv));
 }
 
 int rsvd_b200_id_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q, int s,
                           uint64_t seed, const double *omega, double *I, double *T, rsvd_i64 ldt) {
     READY();
-    return id_rand(A, m, n, lda, k, p, q, s, seed, omega, I, T, ldt);
+    return finish(id_rand(A, m, n, lda, k, p, q, s, seed, omega, I, T, ldt));
 }
 
 int rsvd_b200_id_full_dev(const double *M, rsvd_i64 k, rsvd_i64 n, rsvd_i64 ldm, double *I, double *T, rsvd_i64 ldt) {
     READY();
-    return id_full(M, k, n, ldm, I, T, ldt);
+    return finish(id_full(M, k, n, ldm, I, T, ldt));
 }
 
 int rsvd_b200_id_two_sided_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q,
                                     int s, uint64_t seed, double *Icol, double *Irow, double *T, rsvd_i64 ldt, double *S,
                                     rsvd_i64 lds) {
     READY();
-    return id_two_sided_rand(A, m, n, lda, k, p, q, s, seed, Icol, Irow, T, ldt, S, lds, global_rows(m));
+    return finish(id_two_sided_rand(A, m, n, lda, k, p, q, s, seed, Icol, Irow, T, ldt, S, lds, global_rows(m)));
 }
 
 int rsvd_b200_cur_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q, int s,
                            uint64_t seed, double *C, rsvd_i64 ldc, double *U, rsvd_i64 ldu, double *R, rsvd_i64 ldr) {
     READY();
-    return cur_rand(A, m, n, lda, k, p, q, s, seed, C, ldc, U, ldu, R, ldr, global_rows(m));
+    return finish(cur_rand(A, m, n, lda, k, p, q, s, seed, C, ldc, U, ldu, R, ldr, global_rows(m)));
 }
 
 double rsvd_b200_svd_percent_error_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, const double *U, rsvd_i64 ldu,

@@ -137,27 +137,22 @@ __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ld
                     const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                     const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
                     rotated = 1;
-                    // de Rijk ordering: the rotated column with the larger norm goes to the lower index p, which keeps the
-                    // columns roughly sorted and saves sweeps.  New squared norms: a - t*c and b + t*c.
-                    const bool swap = (a - t * c) < (b + t * c);
-                    double *d0 = swap ? gq : gp, *d1 = swap ? gp : gq;
 #pragma unroll
                     for (int k = 0; k < JR; ++k) {
                         int row = threadIdx.x + k * JT;
                         if (row < n) {
-                            d0[row] = cs * xp[k] - sn * xq[k];
-                            d1[row] = sn * xp[k] + cs * xq[k];
+                            gp[row] = cs * xp[k] - sn * xq[k];
+                            gq[row] = sn * xp[k] + cs * xq[k];
                         }
                     }
                     double *vp = V + (i64)p * ldv, *vq = V + (i64)q * ldv;
-                    double *w0 = swap ? vq : vp, *w1 = swap ? vp : vq;
 #pragma unroll
                     for (int k = 0; k < JR; ++k) {
                         int row = threadIdx.x + k * JT;
                         if (row < n) {
                             double y = __ldcg(vp + row), z = __ldcg(vq + row);
-                            w0[row] = cs * y - sn * z;
-                            w1[row] = sn * y + cs * z;
+                            vp[row] = cs * y - sn * z;
+                            vq[row] = sn * y + cs * z;
                         }
                     }
                 }

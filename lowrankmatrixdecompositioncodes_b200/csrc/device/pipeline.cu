@@ -12,17 +12,34 @@ namespace rsvd {
 
 namespace {
 
-// verbose >= 2: synchronising phase timer (diagnostics only)
+// verbose == 2: synchronising phase timer; verbose == 3: non-synchronising (CUDA events, printed at the end of the call)
 struct Phase {
-    double t0 = 0; bool on;
-    Phase() : on(ctx().verbose >= 2) { if (on) { cudaStreamSynchronize(ctx().stream); t0 = now(); } }
+    double t0 = 0; int mode;
+    std::vector<std::pair<const char *, cudaEvent_t>> ev;
+    Phase() : mode(ctx().verbose) {
+        if (mode == 2) { cudaStreamSynchronize(ctx().stream); t0 = now(); }
+        if (mode == 3) mark("start");
+    }
     static double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+    void mark(const char *what) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx().stream); ev.push_back({what, e}); }
     void lap(const char *what) {
-        if (!on) return;
+        if (mode == 3) { mark(what); return; }
+        if (mode != 2) return;
         cudaStreamSynchronize(ctx().stream);
         double t1 = now();
         fprintf(stderr, "[rsvd_b200]   %-28s %8.3f ms\n", what, (t1 - t0) * 1e3);
         t0 = t1;
+    }
+    ~Phase() {
+        if (mode != 3 || ev.empty()) return;
+        cudaStreamSynchronize(ctx().stream);
+        char line[1024]; int n = snprintf(line, sizeof(line), "[rsvd_b200 r%d]", ctx().rank);
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+            n += snprintf(line + n, sizeof(line) - n, " %s=%.1f", ev[i].first, ms);
+        }
+        fprintf(stderr, "%s\n", line);
+        for (auto &p : ev) cudaEventDestroy(p.second);
     }
 };
 
