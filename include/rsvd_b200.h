@@ -82,6 +82,10 @@ int rsvd_b200_transpose(const double *A, rsvd_i64 lda, double *B, rsvd_i64 ldb, 
 int rsvd_b200_svd_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int vnum,
                            int q, int s, uint64_t seed, const double *omega, double *U, rsvd_i64 ldu, double *S,
                            double *V, rsvd_i64 ldv);
+/* Same as rsvd_b200_svd_rand_dev for a HOST matrix h_A (m x n, ld m; RRA:73-95): the upload into dA (m x n device buffer
+ * supplied by the caller) is pipelined in column blocks with the sketch pass when h_A is pinned memory. */
+int rsvd_b200_svd_rand_host(const double *h_A, double *dA, rsvd_i64 m, rsvd_i64 n, rsvd_i64 k, rsvd_i64 p, int vnum, int q, int s,
+                            uint64_t seed, double *U, rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv);
 /* randQB_pb_new (RRA:1576-1801).  Awork m x n is OVERWRITTEN by the residual A - QB (the reference's private
  * copy, RRA:1630).  Q m x (kstep*nstep_max), B (kstep*nstep_max) x n; *frank = columns actually produced.
  * nstep <= 0: tolerance mode (absolute Frobenius norm < tol, RRA:1773-1775), evaluated on the device. */

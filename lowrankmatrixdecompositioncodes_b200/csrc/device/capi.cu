@@ -6,6 +6,8 @@ int svd_from_q(const double *A, i64 m, i64 n, i64 lda, double *Q, i64 ldq, i64 l
                double *S, double *V, i64 ldv);
 int svd_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int vnum, int q, int s, uint64_t seed,
              const double *omega, double *U, i64 ldu, double *S, double *V, i64 ldv);
+int svd_rand_host(const double *hA, double *dA, i64 m, i64 n, i64 k, i64 p, int vnum, int q, int s, uint64_t seed, double *U, i64 ldu,
+                  double *S, double *V, i64 ldv);
 int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, int q, int s, uint64_t seed, double *Q,
            i64 ldq, double *B, i64 ldb, i64 max_rank, i64 *frank_out);
 int id_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, const double *omega,
@@ -123,6 +125,19 @@ int rsvd_b200_svd_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda
                            rsvd_i64 ldv) {
     READY();
     return finish(svd_rand(A, m, n, lda, k, p, vnum, q, s, seed, omega, U, ldu, S, V, ldv));
+}
+
+int rsvd_b200_svd_rand_host(const double *h_A, double *dA, rsvd_i64 m, rsvd_i64 n, rsvd_i64 k, rsvd_i64 p, int vnum, int q, int s,
+                            uint64_t seed, double *U, rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv) {
+    READY();
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, h_A) != cudaSuccess || a.type != cudaMemoryTypeHost) {
+        (void)cudaGetLastError();
+        // pageable source: staged upload, then the ordinary device-resident algorithm
+        if (rsvd_b200_h2d(dA, h_A, m * n)) return g_status;
+        return finish(svd_rand(dA, m, n, m, k, p, vnum, q, s, seed, nullptr, U, ldu, S, V, ldv));
+    }
+    return finish(svd_rand_host(h_A, dA, m, n, k, p, vnum, q, s, seed, U, ldu, S, V, ldv));
 }
 
 int rsvd_b200_randqb_dev(double *Awork, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 kstep, rsvd_i64 nstep, double tol,

@@ -111,7 +111,8 @@ int lu_solve(double *A, i64 lda, i64 n, double *B, i64 ldb, i64 nrhs);        //
 // Q (m x l, ld) <- orthonormal basis of range(Y); in place. If R != nullptr also returns R (l x l upper).
 // sharded = true: Y is this rank's row block of a row-partitioned panel (Gram matrices are all-reduced);
 // sharded = false: Y is replicated on every rank (no communication).
-void orthonormalize(double *Y, i64 ldy, i64 m, i64 l, double *R, i64 ldr, bool sharded = true);
+// loose = true: the caller only needs a well-conditioned basis of the same range (intermediate power-iteration steps).
+void orthonormalize(double *Y, i64 ldy, i64 m, i64 l, double *R, i64 ldr, bool sharded = true, bool loose = false);
 int potrf_upper(double *G, i64 ldg, i64 n);       // in-place upper Cholesky G = R^T R; returns 0 or failing column+1
 void trtri_upper(const double *R, i64 ldr, i64 n, double *Rinv, i64 ldi); // Rinv = R^{-1}
 

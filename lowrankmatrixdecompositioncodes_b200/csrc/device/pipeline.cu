@@ -144,24 +144,29 @@ int svd_from_q(const double *A, i64 m, i64 n, i64 lda, double *Q, i64 ldq, i64 l
 // ---------------------------------------------------------------------------------------------------------
 // low_rank_svd_rand_decomp_fixed_rank (RRA:73-234)
 // ---------------------------------------------------------------------------------------------------------
-int svd_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int vnum, int q, int s, uint64_t seed,
-             const double *omega, double *U, i64 ldu, double *S, double *V, i64 ldv) {
+// `Y0` (optional): an already computed sketch A*Omega (m x l, ld m) — used when the upload of A was pipelined with it.
+static int svd_rand_impl(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int vnum, int q, int s, uint64_t seed,
+                         const double *omega, DBuf *Y0, double *U, i64 ldu, double *S, double *V, i64 ldv) {
     ensure_init();
     if (!ctx().inited) return 1;
     const i64 l = k + p;
     if (k <= 0 || p < 0 || l > n || s <= 0) { set_error("rsvd_b200: invalid parameters k=%lld p=%lld s=%d (need 0 < k+p <= n, s > 0)", (long long)k, (long long)p, s); return 1; }
-    DBuf Y((size_t)m * l), Z((size_t)n * l);
+    DBuf Y, Z((size_t)n * l);
     Phase ph;
-    if (omega) mm('N', 'N', m, l, n, 1.0, A, lda, omega, n, 0.0, Y.p, m);           // Y = M RN (RRA:95)
-    else sketch('N', m, l, n, A, lda, seed, 1, n, 0, Y.p, m);                       // RN generated in the B-operand producer
+    if (Y0) Y = std::move(*Y0);
+    else {
+        Y.alloc((size_t)m * l);
+        if (omega) mm('N', 'N', m, l, n, 1.0, A, lda, omega, n, 0.0, Y.p, m);       // Y = M RN (RRA:95)
+        else sketch('N', m, l, n, A, lda, seed, 1, n, 0, Y.p, m);                   // RN generated in the B-operand producer
+    }
     ph.lap("Y = A Omega (sketch)");
     for (int j = 1; j < q; ++j) {                                                   // NOTE j < q (RRA:101)
-        if ((2 * j - 2) % s == 0) orthonormalize(Y.p, m, m, l, nullptr, 0, true);   // RRA:106
+        if ((2 * j - 2) % s == 0) orthonormalize(Y.p, m, m, l, nullptr, 0, true, true);   // RRA:106 (stabilisation only)
         ph.lap("orth(Y)");
         mm('T', 'N', n, l, m, 1.0, A, lda, Y.p, m, 0.0, Z.p, n);                    // Z = M^T Y (RRA:108/112)
         allreduce_sum(Z.p, (size_t)n * l);
         ph.lap("Z = A^T Y");
-        if ((2 * j - 1) % s == 0) orthonormalize(Z.p, n, n, l, nullptr, 0, false);  // RRA:118
+        if ((2 * j - 1) % s == 0) orthonormalize(Z.p, n, n, l, nullptr, 0, false, true);  // RRA:118 (stabilisation only)
         ph.lap("orth(Z)");
         mm('N', 'N', m, l, n, 1.0, A, lda, Z.p, n, 0.0, Y.p, m);                    // Y = M Z (RRA:120/124)
         ph.lap("Y = A Z");
@@ -170,6 +175,46 @@ int svd_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int vnum, int
     orthonormalize(Y.p, m, m, l, nullptr, 0, true);                                 // Q (RRA:129-130)
     ph.lap("Q = orth(Y)");
     return svd_from_q(A, m, n, lda, Y.p, m, l, k, vnum, U, ldu, S, V, ldv);
+}
+
+int svd_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int vnum, int q, int s, uint64_t seed,
+             const double *omega, double *U, i64 ldu, double *S, double *V, i64 ldv) {
+    return svd_rand_impl(A, m, n, lda, k, p, vnum, q, s, seed, omega, nullptr, U, ldu, S, V, ldv);
+}
+
+// Same algorithm from a HOST matrix (pinned memory): A is uploaded in column blocks on the copy stream while the sketch
+// pass consumes the blocks that have landed (Y += A(:,blk) * Omega(blk,:), Omega generated in the kernel), so the first of
+// the 2q passes hides behind the PCIe transfer.  dA (m x n, ld m) receives the uploaded matrix.
+int svd_rand_host(const double *hA, double *dA, i64 m, i64 n, i64 k, i64 p, int vnum, int q, int s, uint64_t seed,
+                  double *U, i64 ldu, double *S, double *V, i64 ldv) {
+    ensure_init();
+    Ctx &c = ctx();
+    if (!c.inited) return 1;
+    const i64 l = k + p;
+    if (k <= 0 || p < 0 || l > n || s <= 0) { set_error("rsvd_b200: invalid parameters k=%lld p=%lld s=%d (need 0 < k+p <= n, s > 0)", (long long)k, (long long)p, s); return 1; }
+    DBuf Y((size_t)m * l);
+    i64 cw = ((i64)(384ll << 20) / (8 * m)) / 16 * 16;     // ~384 MB column blocks, multiples of the GEMM's k-tile
+    if (cw < 256) cw = 256;
+    const int nchunks = (int)((n + cw - 1) / cw);
+    std::vector<cudaEvent_t> ev((size_t)nchunks);
+    for (int i = 0; i < nchunks; ++i) {
+        const i64 c0 = (i64)i * cw, w = std::min(cw, n - c0);
+        RSVD_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        RSVD_CUDA(cudaMemcpyAsync(dA + c0 * m, hA + c0 * m, (size_t)w * m * 8, cudaMemcpyHostToDevice, c.copy_stream));
+        RSVD_CUDA(cudaEventRecord(ev[i], c.copy_stream));
+    }
+    for (int i = 0; i < nchunks; ++i) {
+        const i64 c0 = (i64)i * cw, w = std::min(cw, n - c0);
+        RSVD_CUDA(cudaStreamWaitEvent(c.stream, ev[i], 0));
+        Gemm g;
+        g.ta = 'N'; g.tb = 'N'; g.m = m; g.n = l; g.k = w; g.A = dA + c0 * m; g.lda = m; g.C = Y.p; g.ldc = m;
+        g.beta = (i == 0) ? 0.0 : 1.0;
+        g.philox = true; g.seed = seed; g.ph_sk = 1; g.ph_sc = n; g.ph_off = c0;     // Omega(c0 + kk, j) = normal(seed, c0 + kk + j*n)
+        gemm(g);
+    }
+    RSVD_CUDA(cudaStreamSynchronize(c.stream));
+    for (auto &e : ev) cudaEventDestroy(e);
+    return svd_rand_impl(dA, m, n, m, k, p, vnum, q, s, seed, nullptr, &Y, U, ldu, S, V, ldv);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -191,10 +236,10 @@ int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, i
         const i64 c0 = kstep * step;
         sketch('N', m, kstep, n, A, lda, seed, 1, n, c0 * n, Yp.p, m);              // Yp = A RN(:,block) (RRA:1643-1644)
         for (int j = 1; j <= q; ++j) {                                              // NOTE j <= q (RRA:1652)
-            if ((2 * j - 2) % s == 0) orthonormalize(Yp.p, m, m, kstep, nullptr, 0, true);   // RRA:1655
+            if ((2 * j - 2) % s == 0) orthonormalize(Yp.p, m, m, kstep, nullptr, 0, true, true);   // RRA:1655
             mm('T', 'N', n, kstep, m, 1.0, A, lda, Yp.p, m, 0.0, W.p, n);           // AtQp (RRA:1657-1658 / 1665)
             allreduce_sum(W.p, (size_t)n * kstep);
-            if ((2 * j - 1) % s == 0) orthonormalize(W.p, n, n, kstep, nullptr, 0, false);   // RRA:1673
+            if ((2 * j - 1) % s == 0) orthonormalize(W.p, n, n, kstep, nullptr, 0, false, true);   // RRA:1673
             mm('N', 'N', m, kstep, n, 1.0, A, lda, W.p, n, 0.0, Yp.p, m);           // Yp = A AtQp2 (RRA:1674 / 1681)
         }
         orthonormalize(Yp.p, m, m, kstep, nullptr, 0, true);                        // Qp (RRA:1690)

@@ -54,6 +54,7 @@ SIGNATURES = {
     "rsvd_b200_frob_norm": (C.c_double, [dp, i64, i64, i64]),
     "rsvd_b200_transpose": (C.c_int, [dp, i64, dp, i64, i64, i64]),
     "rsvd_b200_svd_rand_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, u64, dp, dp, i64, dp, dp, i64]),
+    "rsvd_b200_svd_rand_host": (C.c_int, [C.c_void_p, dp, i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, u64, dp, i64, dp, dp, i64]),
     "rsvd_b200_randqb_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_double, C.c_int, C.c_int, u64, dp, i64, dp, i64, C.POINTER(i64)]),
     "rsvd_b200_svd_from_q_dev": (C.c_int, [dp, i64, i64, i64, dp, i64, i64, i64, C.c_int, dp, i64, dp, dp, i64]),
     "rsvd_b200_id_rand_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, dp, dp, dp, i64]),
