@@ -1,0 +1,124 @@
+"""tools/large_configs.py — BASELINE configs[2] (blockrand QB, tolerance mode) and configs[3] (two-sided ID + CUR) at
+(scaled) benchmark sizes on one B200, device resident, matrix generated in HBM; prints times and streamed error checks.
+    python tools/large_configs.py c3 [rows] | c4 [rows] | abi64"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+import lowrankmatrixdecompositioncodes_b200 as pkg  # noqa: E402
+from lowrankmatrixdecompositioncodes_b200 import device as D, native  # noqa: E402
+
+lib = native.dev()
+assert lib.rsvd_b200_init(0) == 0
+what = sys.argv[1] if len(sys.argv) > 1 else "c3"
+
+
+def gen(m, n, r=1280, lo=-3.0, noise=1e-8, seed=0):
+    """A = X diag(sigma) W^T + noise, sigma = logspace(1, lo, r), built in HBM in column slabs (torch only generates data)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    X = torch.randn((m, r), dtype=torch.float64, device="cuda", generator=g) / m ** 0.5
+    W = torch.randn((n, r), dtype=torch.float64, device="cuda", generator=g) / n ** 0.5
+    sig = torch.logspace(1, lo, r, dtype=torch.float64, device="cuda")
+    A = torch.empty((n, m), dtype=torch.float64, device="cuda")
+    step = 2048
+    for j0 in range(0, n, step):
+        j1 = min(n, j0 + step)
+        torch.matmul(W[j0:j1] * sig, X.t(), out=A[j0:j1])
+        A[j0:j1] += noise * torch.randn((j1 - j0, m), dtype=torch.float64, device="cuda", generator=g)
+    del X, W
+    torch.cuda.synchronize()
+    return A, sig
+
+
+def sync():
+    lib.rsvd_b200_sync()
+    torch.cuda.synchronize()
+
+
+if what == "c3":
+    m = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
+    n, kstep, q, s = 50000, 200, 2, 1
+    A, sig = gen(m, n)
+    normA = lib.rsvd_b200_frob_norm(A.data_ptr(), m, m, n)
+    tol = float(torch.sqrt((sig[600:] ** 2).sum()).item()) * 1.5     # reached after ~3 blocks of 200
+    cap = 2000
+    Q = torch.zeros((cap, m), dtype=torch.float64, device="cuda")
+    B = torch.zeros((n, cap), dtype=torch.float64, device="cuda")
+    fr = C.c_longlong(0)
+    print("C3: randQB_pb_new tolerance mode on %d x %d (%.1f GB), kstep=%d q=%d, ||A||_F=%.4f, TOL=%.4g (absolute)" % (m, n, 8e-9 * m * n, kstep, q, normA, tol), flush=True)
+    lib.rsvd_b200_set_option(b"verbose", 1)
+    sync()
+    t0 = time.time()
+    native.check(lib.rsvd_b200_randqb_dev(A.data_ptr(), m, n, m, kstep, 0, tol, q, s, 777, Q.data_ptr(), m, B.data_ptr(), cap, C.byref(fr)))
+    sync()
+    dt = time.time() - t0
+    f = int(fr.value)
+    res = lib.rsvd_b200_frob_norm(A.data_ptr(), m, m, n)     # A now holds the residual A - QB
+    passes = (f // kstep) * (2 * q + 3)
+    print("   frank=%d  time %.3f s  ||A-QB||_F=%.4g (< TOL: %s)  %.1f TFLOP/s over %d width-%d passes" %
+          (f, dt, res, res < tol, passes * 2.0 * m * n * kstep / dt / 1e12, passes, kstep), flush=True)
+    Qf = Q[:f]
+    print("   ||Q^T Q - I||_max = %.2e" % (Qf @ Qf.t() - torch.eye(f, dtype=torch.float64, device="cuda")).abs().max().item())
+
+elif what == "c4":
+    m = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
+    n, k, p, q, s = 50000, 1000, 20, 2, 1
+    A, sig = gen(m, n, r=1536, lo=-2.0)
+    print("C4: id_two_sided_rand + cur_rand on %d x %d (%.1f GB), k=%d p=%d q=%d" % (m, n, 8e-9 * m * n, k, p, q), flush=True)
+    Icol = torch.empty(n, dtype=torch.float64, device="cuda"); Irow = torch.empty(m, dtype=torch.float64, device="cuda")
+    T = torch.empty((n - k, k), dtype=torch.float64, device="cuda"); Sm = torch.empty((m - k, k), dtype=torch.float64, device="cuda")
+    lib.rsvd_b200_set_option(b"verbose", 1)
+    sync()
+    t0 = time.time()
+    native.check(lib.rsvd_b200_id_two_sided_rand_dev(A.data_ptr(), m, n, m, k, p, q, s, 777, Icol.data_ptr(), Irow.data_ptr(), T.data_ptr(), k, Sm.data_ptr(), k))
+    sync()
+    dt = time.time() - t0
+    flops = (1 + 2 * q) * 2.0 * m * n * (k + p)
+    print("   two-sided ID: %.3f s  (%.1f TFLOP/s over the %d sketch/power passes alone)" % (dt, flops / dt / 1e12, 1 + 2 * q), flush=True)
+    ic, ir = Icol.long(), Irow.long()
+    assert torch.equal(torch.sort(ic).values, torch.arange(n, device="cuda")) and torch.equal(torch.sort(ir).values, torch.arange(m, device="cuda"))
+    # column-ID error on a row sample:  A(rows, Icol) ~ A(rows, Icol[:k]) [I T]
+    rows = torch.randperm(m, device="cuda")[:4096]
+    As = A.t()[rows]                                   # 4096 x n
+    Ck = As[:, ic[:k]]
+    err = (As[:, ic[k:]] - Ck @ T.t()).norm() / As.norm()
+    opt = torch.sqrt((sig[k:] ** 2).sum()) / torch.sqrt((sig ** 2).sum())
+    print("   column ID rel. error on 4096 sampled rows: %.4e  (optimal rank-%d: %.4e)" % (err.item(), k, opt.item()), flush=True)
+    del T, Sm
+    Cm = D.new_cm(m, k); Um = D.new_cm(k, k); Rm = D.new_cm(k, n)
+    sync()
+    t0 = time.time()
+    native.check(lib.rsvd_b200_cur_rand_dev(A.data_ptr(), m, n, m, k, p, q, s, 777, Cm.data_ptr(), m, Um.data_ptr(), k, Rm.data_ptr(), k))
+    sync()
+    dt = time.time() - t0
+    print("   CUR (includes its own two-sided ID): %.3f s" % dt, flush=True)
+    Cs = Cm.t()[rows]                                  # 4096 x k
+    err = (As - Cs @ Um.t() @ Rm.t()).norm() / As.norm()
+    print("   CUR rel. error on the row sample: %.4e" % err.item(), flush=True)
+
+elif what == "abi64":
+    # int64 ABI end to end with m*n > 2^31 elements (the reason multi_core_mkl_code_64bit exists)
+    m, n, k, p = 72000, 30000, 200, 20
+    api = pkg.Api(64)
+    M = api.lib.matrix_new(m, n)
+    A, sig = gen(m, n, r=512, lo=-3.0)
+    native.check(lib.rsvd_b200_d2h(C.cast(M.contents.d, C.c_void_p), A.data_ptr(), m * n))
+    del A
+    torch.cuda.empty_cache()
+    print("abi64: %d x %d = %.3g elements (> 2^31), %.1f GB host matrix" % (m, n, float(m) * n, 8e-9 * m * n), flush=True)
+    Um, Sm, Vm = api.PM(), api.PM(), api.PM()
+    fr = api.I(0)
+    t0 = time.time()
+    api.lib.low_rank_svd_rand_decomp_fixed_rank(M, k, p, 1, 2, 1, C.byref(fr), C.byref(Um), C.byref(Sm), C.byref(Vm))
+    dt = time.time() - t0
+    api.check()
+    S = api.from_mat(Sm, free=False)
+    rel = np.max(np.abs(np.diag(S) - sig[:k].cpu().numpy()) / sig[:k].cpu().numpy())
+    api.lib.use_low_rank_svd_for_approximation(M, Um, Sm, Vm)
+    print("   API call %.3f s; max rel deviation of sigma from the construction: %.2e; percent error %.4f" % (dt, rel, api.lib.rsvd_b200_api_last_percent_error()), flush=True)
+print("status:", lib.rsvd_b200_status(), lib.rsvd_b200_last_error())
