@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 
 M_PER_GPU, N_COLS, K, P, Q, S_ORTH, VNUM = 50000, 20000, 500, 20, 2, 1, 1
 WORKLOAD = "low_rank_svd_rand_decomp_fixed_rank 50000x20000 fp64 (per GPU), k=500 p=20 q=2 s=1 vnum=1 (BASELINE configs[1])"
+# --config c5: BASELINE configs[4] (the north-star target): 1,000,000 x 100,000 over 8 GPUs = 125,000 rows (100 GB) per GPU
+C5 = dict(rows=125000, n=100000, k=1000, p=50,
+          workload="low_rank_svd_rand_decomp_fixed_rank 1,000,000x100,000 fp64 over 8 GPUs (125000 rows = 100 GB per GPU), k=1000 p=50 q=2 (BASELINE configs[4])")
 METRIC = "randSVD FP64 TFLOP/s (GEMM flops 2q*2mn(k+p) / time-to-solution)"
 
 
@@ -161,8 +164,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the isolated per-pass timing (used under ncu)")
-    ap.add_argument("--rows", type=int, default=M_PER_GPU, help="rows per GPU (default: the BASELINE workload)")
+    ap.add_argument("--rows", type=int, default=None, help="rows per GPU (default: the BASELINE workload)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c5"], help="c2 = BASELINE configs[1] per GPU (default); c5 = configs[4] (device-resident only)")
     args = ap.parse_args()
+    global N_COLS, K, P, WORKLOAD
+    if args.config == "c5":
+        N_COLS, K, P, WORKLOAD = C5["n"], C5["k"], C5["p"], C5["workload"]
+        args.no_e2e = True          # 100 GB per rank does not fit the host; the matrix exists only in HBM
+        args.no_cpu_baseline = True
+        if args.rows is None:
+            args.rows = C5["rows"]
+    if args.rows is None:
+        args.rows = M_PER_GPU
     # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner, the reference's progress
     # printf) are redirected to stderr until the line is ready
     sys.stdout.flush()
@@ -217,8 +230,10 @@ def main():
     W = torch.randn((n, r), dtype=torch.float64, device="cuda", generator=gw) / (n ** 0.5)
     sig = torch.logspace(1, -3, r, dtype=torch.float64, device="cuda")
     A_cm = torch.empty((n, m), dtype=torch.float64, device="cuda")          # column-major m x n
-    torch.matmul(W * sig, X.t(), out=A_cm)
-    A_cm += 1e-6 * torch.randn((n, m), dtype=torch.float64, device="cuda", generator=g)
+    for j0 in range(0, n, 4096):
+        j1 = min(n, j0 + 4096)
+        torch.matmul(W[j0:j1] * sig, X.t(), out=A_cm[j0:j1])
+        A_cm[j0:j1] += 1e-6 * torch.randn((j1 - j0, m), dtype=torch.float64, device="cuda", generator=g)
     del X, W
     U = D.new_cm(m, K); V = D.new_cm(n, K)
     Sv = torch.empty(K, dtype=torch.float64, device="cuda")
