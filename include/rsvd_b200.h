@@ -99,6 +99,18 @@ int rsvd_b200_id_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda,
                           uint64_t seed, const double *omega, double *I, double *T, rsvd_i64 ldt);
 /* id_decomp_fixed_rank_or_prec, k == min(m,n) branch (RRA:1830-1850): full pivoted QR of M (k x n). */
 int rsvd_b200_id_full_dev(const double *M, rsvd_i64 k, rsvd_i64 n, rsvd_i64 ldm, double *I, double *T, rsvd_i64 ldt);
+/* pivoted QR of M (r x n) + T = R11(k x k)^{-1} R12: id_rand_decomp_fromQB (oneapi_code/rank_revealing_algorithms_one_api.c:421-444)
+ * and the B-factor step of id_blockrand_decomp_fixed_rank_or_prec (RRA:1996-2020). */
+int rsvd_b200_id_qr_dev(const double *M, rsvd_i64 r, rsvd_i64 n, rsvd_i64 ldm, rsvd_i64 k, double *I, double *T, rsvd_i64 ldt);
+/* row ID of M(:, Icol(1:k)) — second half of every two-sided ID (RRA:2071-2078, 2098-2107). */
+int rsvd_b200_id_rows_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, const double *Icol, rsvd_i64 k, double *Irow, double *S,
+                          rsvd_i64 lds);
+/* CUR factors from a two-sided ID (RRA:2200-2252, 2274-2326). */
+int rsvd_b200_cur_from_id_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, const double *Icol, const double *Irow, const double *T,
+                              rsvd_i64 ldt, rsvd_i64 k, double *C, rsvd_i64 ldc, double *U, rsvd_i64 ldu, double *R, rsvd_i64 ldr);
+/* low_rank_svd_rand_decomp_fromQB (oneapi_code/rank_revealing_algorithms_one_api.c:244-304, FP64): SVD factors from Q (m x l), B (l x n). */
+int rsvd_b200_svd_from_qb_dev(const double *Q, rsvd_i64 m, rsvd_i64 ldq, const double *B, rsvd_i64 l, rsvd_i64 n, rsvd_i64 ldb, double *U,
+                              rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv);
 /* id_two_sided_rand_decomp_fixed_rank (RRA:2060-2082). Icol n, Irow m, T k x (n-k), S k x (m-k). */
 int rsvd_b200_id_two_sided_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q,
                                     int s, uint64_t seed, double *Icol, double *Irow, double *T, rsvd_i64 ldt,

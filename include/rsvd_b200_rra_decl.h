@@ -31,6 +31,18 @@ void id_two_sided_rand_decomp_fixed_rank(mat *M, RSVD_INT k, RSVD_INT p, RSVD_IN
 /* ---- CUR (RRH:88) ---- */
 void cur_rand_decomp_fixed_rank(mat *M, RSVD_INT k, RSVD_INT p, RSVD_INT q, RSVD_INT s, mat **C, mat **U, mat **R);
 
+/* ---- block-randomized ID / two-sided ID / CUR on top of the device QB (RRH:71, 81, 91) ---- */
+void id_blockrand_decomp_fixed_rank_or_prec(mat *M, RSVD_INT k, RSVD_INT p, double TOL, RSVD_INT kstep, RSVD_INT q, RSVD_INT s,
+                                            RSVD_INT *frank, vec **I, mat **T);
+void id_two_sided_blockrand_decomp_fixed_rank_or_prec(mat *M, RSVD_INT k, RSVD_INT p, double TOL, RSVD_INT kstep, RSVD_INT q,
+                                                      RSVD_INT s, RSVD_INT *frank, vec **Icol, vec **Irow, mat **T, mat **S);
+void cur_blockrand_decomp_fixed_rank_or_prec(mat *M, RSVD_INT k, RSVD_INT p, double TOL, RSVD_INT kstep, RSVD_INT q, RSVD_INT s,
+                                             RSVD_INT *frank, mat **C, mat **U, mat **R);
+
+/* ---- SVD / ID from an existing QB (oneapi_code/rank_revealing_algorithms_one_api.h:6,10), FP64 ---- */
+void low_rank_svd_rand_decomp_fromQB(mat *Q, mat *B, mat **U, mat **S, mat **V);
+void id_rand_decomp_fromQB(mat *Q, mat *B, vec **I, mat **T);
+
 /* ---- evaluation helpers used by every driver (RRH:95-110): print 100*||M - approx||_F/||M||_F ---- */
 void use_low_rank_svd_for_approximation(mat *M, mat *U, mat *S, mat *V);
 void use_QB_decomp_for_approximation(mat *M, mat *Q, mat *B);

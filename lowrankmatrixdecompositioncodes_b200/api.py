@@ -42,6 +42,11 @@ class Api:
         L.id_decomp_fixed_rank_or_prec.argtypes = [PM, I, C.c_double, C.POINTER(I), PPV, PPM]
         L.id_two_sided_rand_decomp_fixed_rank.argtypes = [PM, I, I, I, I, PPV, PPV, PPM, PPM]
         L.cur_rand_decomp_fixed_rank.argtypes = [PM, I, I, I, I, PPM, PPM, PPM]
+        L.id_blockrand_decomp_fixed_rank_or_prec.argtypes = [PM, I, I, C.c_double, I, I, I, C.POINTER(I), PPV, PPM]
+        L.id_two_sided_blockrand_decomp_fixed_rank_or_prec.argtypes = [PM, I, I, C.c_double, I, I, I, C.POINTER(I), PPV, PPV, PPM, PPM]
+        L.cur_blockrand_decomp_fixed_rank_or_prec.argtypes = [PM, I, I, C.c_double, I, I, I, C.POINTER(I), PPM, PPM, PPM]
+        L.low_rank_svd_rand_decomp_fromQB.argtypes = [PM, PM, PPM, PPM, PPM]
+        L.id_rand_decomp_fromQB.argtypes = [PM, PM, PPV, PPM]
         L.pivotedQR_mkl.argtypes = [PM, PPM, PPM, PPV]
         L.matrix_load_from_binary_file.restype = PM
         L.matrix_load_from_binary_file.argtypes = [C.c_char_p]
@@ -169,6 +174,59 @@ class Api:
         self.lib.cur_rand_decomp_fixed_rank(M, k, p, q, s, C.byref(Cm), C.byref(U), C.byref(R))
         self.lib.matrix_delete(M)
         out = self.from_mat(Cm), self.from_mat(U), self.from_mat(R)
+        self.check()
+        return out
+
+
+    def id_blockrand(self, A, k, p, TOL, kstep, q, s, seed=777):
+        self.set_seed(seed)
+        M = self.to_mat(A)
+        I_, T = self.PV(), self.PM()
+        frank = self.I(0)
+        self.lib.id_blockrand_decomp_fixed_rank_or_prec(M, k, p, float(TOL), kstep, q, s, C.byref(frank), C.byref(I_), C.byref(T))
+        self.lib.matrix_delete(M)
+        out = int(frank.value), self.from_vec(I_), self.from_mat(T)
+        self.check()
+        return out
+
+    def id_two_sided_blockrand(self, A, k, p, TOL, kstep, q, s, seed=777):
+        self.set_seed(seed)
+        M = self.to_mat(A)
+        Ic, Ir, T, S = self.PV(), self.PV(), self.PM(), self.PM()
+        frank = self.I(0)
+        self.lib.id_two_sided_blockrand_decomp_fixed_rank_or_prec(M, k, p, float(TOL), kstep, q, s, C.byref(frank), C.byref(Ic), C.byref(Ir),
+                                                                  C.byref(T), C.byref(S))
+        self.lib.matrix_delete(M)
+        out = int(frank.value), self.from_vec(Ic), self.from_vec(Ir), self.from_mat(T), self.from_mat(S)
+        self.check()
+        return out
+
+    def cur_blockrand(self, A, k, p, TOL, kstep, q, s, seed=777):
+        self.set_seed(seed)
+        M = self.to_mat(A)
+        Cm, U, R = self.PM(), self.PM(), self.PM()
+        frank = self.I(0)
+        self.lib.cur_blockrand_decomp_fixed_rank_or_prec(M, k, p, float(TOL), kstep, q, s, C.byref(frank), C.byref(Cm), C.byref(U), C.byref(R))
+        self.lib.matrix_delete(M)
+        out = int(frank.value), self.from_mat(Cm), self.from_mat(U), self.from_mat(R)
+        self.check()
+        return out
+
+    def svd_from_qb(self, Q, B):
+        Qm, Bm = self.to_mat(Q), self.to_mat(B)
+        U, S, V = self.PM(), self.PM(), self.PM()
+        self.lib.low_rank_svd_rand_decomp_fromQB(Qm, Bm, C.byref(U), C.byref(S), C.byref(V))
+        self.lib.matrix_delete(Qm); self.lib.matrix_delete(Bm)
+        out = self.from_mat(U), self.from_mat(S), self.from_mat(V)
+        self.check()
+        return out
+
+    def id_from_qb(self, Q, B):
+        Qm, Bm = self.to_mat(Q), self.to_mat(B)
+        I_, T = self.PV(), self.PM()
+        self.lib.id_rand_decomp_fromQB(Qm, Bm, C.byref(I_), C.byref(T))
+        self.lib.matrix_delete(Qm); self.lib.matrix_delete(Bm)
+        out = self.from_vec(I_), self.from_mat(T)
         self.check()
         return out
 

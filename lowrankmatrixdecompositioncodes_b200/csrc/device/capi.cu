@@ -13,6 +13,11 @@ int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, i
 int id_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, const double *omega,
             double *I, double *T, i64 ldt);
 int id_full(const double *M, i64 k, i64 n, i64 ldm, double *I, double *T, i64 ldt);
+int id_qr(const double *M, i64 r, i64 n, i64 ldm, i64 k, double *I, double *T, i64 ldt);
+int id_rows(const double *A, i64 m, i64 n, i64 lda, const double *Icol, i64 k, double *Irow, double *S, i64 lds, i64 m_global);
+int cur_from_id(const double *A, i64 m, i64 n, i64 lda, const double *Icol, const double *Irow, const double *T, i64 ldt, i64 k,
+                double *Cm, i64 ldc, double *U, i64 ldu, double *R, i64 ldr);
+int svd_from_qb(const double *Q, i64 m, i64 ldq, const double *B, i64 l, i64 n, i64 ldb, double *U, i64 ldu, double *S, double *V, i64 ldv);
 int id_two_sided_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, double *Icol,
                       double *Irow, double *T, i64 ldt, double *S, i64 lds, i64 m_global);
 int cur_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, double *Cm, i64 ldc,
@@ -162,6 +167,29 @@ int rsvd_b200_id_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda,
 int rsvd_b200_id_full_dev(const double *M, rsvd_i64 k, rsvd_i64 n, rsvd_i64 ldm, double *I, double *T, rsvd_i64 ldt) {
     READY();
     return finish(id_full(M, k, n, ldm, I, T, ldt));
+}
+
+int rsvd_b200_id_qr_dev(const double *M, rsvd_i64 r, rsvd_i64 n, rsvd_i64 ldm, rsvd_i64 k, double *I, double *T, rsvd_i64 ldt) {
+    READY();
+    return finish(id_qr(M, r, n, ldm, k, I, T, ldt));
+}
+
+int rsvd_b200_id_rows_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, const double *Icol, rsvd_i64 k, double *Irow, double *S,
+                          rsvd_i64 lds) {
+    READY();
+    return finish(id_rows(A, m, n, lda, Icol, k, Irow, S, lds, global_rows(m)));
+}
+
+int rsvd_b200_cur_from_id_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, const double *Icol, const double *Irow, const double *T,
+                              rsvd_i64 ldt, rsvd_i64 k, double *C, rsvd_i64 ldc, double *U, rsvd_i64 ldu, double *R, rsvd_i64 ldr) {
+    READY();
+    return finish(cur_from_id(A, m, n, lda, Icol, Irow, T, ldt, k, C, ldc, U, ldu, R, ldr));
+}
+
+int rsvd_b200_svd_from_qb_dev(const double *Q, rsvd_i64 m, rsvd_i64 ldq, const double *B, rsvd_i64 l, rsvd_i64 n, rsvd_i64 ldb, double *U,
+                              rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv) {
+    READY();
+    return finish(svd_from_qb(Q, m, ldq, B, l, n, ldb, U, ldu, S, V, ldv));
 }
 
 int rsvd_b200_id_two_sided_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q,

@@ -333,10 +333,24 @@ int id_full(const double *M, i64 k, i64 n, i64 ldm, double *I, double *T, i64 ld
     return g_status;
 }
 
-int id_two_sided_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed,
-                      double *Icol, double *Irow, double *T, i64 ldt, double *S, i64 lds, i64 m_global) {
+// pivoted QR of an r x n matrix M (copied), I, T = R11(k x k)^{-1} R12   (id_rand_decomp_fromQB, oneapi_code/
+// rank_revealing_algorithms_one_api.c:421-444; the B-factor step of id_blockrand_decomp_fixed_rank_or_prec, RRA:1996-2020)
+int id_qr(const double *M, i64 r, i64 n, i64 ldm, i64 k, double *I, double *T, i64 ldt) {
+    ensure_init();
+    if (!ctx().inited) return 1;
+    if (k > std::min(r, n) || k <= 0) { set_error("rsvd_b200: id_qr needs 0 < k <= min(rows, cols) (k=%lld, %lld x %lld)", (long long)k, (long long)r, (long long)n); return 1; }
+    DBuf W((size_t)r * n);
+    copy_matrix(M, ldm, W.p, r, r, n);
+    id_tail(W.p, r, r, n, k, I, T, ldt);
+    return g_status;
+}
+
+// row ID of MI = A(:, Icol(1:k))  (RRA:2071-2078 -> RRA:1830-1850): Irow (m_global), S k x (m_global - k)
+int id_rows(const double *A, i64 m, i64 n, i64 lda, const double *Icol, i64 k, double *Irow, double *S, i64 lds, i64 m_global) {
+    ensure_init();
     Ctx &c = ctx();
-    if (id_rand(A, m, n, lda, k, p, q, s, seed, nullptr, Icol, T, ldt)) return 1;  // RRA:2068
+    if (!c.inited) return 1;
+    (void)n;
     DBuf MI((size_t)m * k);
     gather_cols(A, lda, m, Icol, k, MI.p, m);                                        // MI = M(:, Icol(1:k)) (RRA:2073)
     if (c.world == 1) {
@@ -356,34 +370,38 @@ int id_two_sided_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int 
     return g_status;
 }
 
-int cur_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed,
-             double *Cm, i64 ldc, double *U, i64 ldu, double *R, i64 ldr, i64 m_global) {
+int id_two_sided_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed,
+                      double *Icol, double *Irow, double *T, i64 ldt, double *S, i64 lds, i64 m_global) {
+    if (id_rand(A, m, n, lda, k, p, q, s, seed, nullptr, Icol, T, ldt)) return 1;  // RRA:2068
+    return id_rows(A, m, n, lda, Icol, k, Irow, S, lds, m_global);
+}
+
+// CUR from a two-sided ID (RRA:2200-2252): C = M(:,Icol(1:k)), R = M(Irow(1:k),:), U = ((R R^T)^{-1} R V)^T, V = [I;T^T](Icol^{-1},:)
+int cur_from_id(const double *A, i64 m, i64 n, i64 lda, const double *Icol, const double *Irow, const double *T, i64 ldt, i64 k,
+                double *Cm, i64 ldc, double *U, i64 ldu, double *R, i64 ldr) {
     ensure_init();
     Ctx &c = ctx();
     if (!c.inited) return 1;
-    DBuf Icol((size_t)n), Irow((size_t)m_global), T((size_t)k * max((i64)1, n - k)), S((size_t)k * max((i64)1, m_global - k));
-    if (id_two_sided_rand(A, m, n, lda, k, p, q, s, seed, Icol.p, Irow.p, T.p, k, S.p, k, m_global)) return 1;   // RRA:2198
-    S.release();
     DBuf V((size_t)n * k);
     {
         i64 total = n * k;
         int blocks = (int)min((i64)c.sms * 8, (total + 255) / 256);
-        build_v_kernel<<<max(blocks, 1), 256, 0, c.stream>>>(Icol.p, T.p, k, n, k, V.p, n);   // RRA:2200-2219
+        build_v_kernel<<<max(blocks, 1), 256, 0, c.stream>>>(Icol, T, ldt, n, k, V.p, n);   // RRA:2200-2219
         count_launch();
     }
     {   // R = M(Irow(1:k), :)  (RRA:2230-2231)
         i64 total = k * n;
         int blocks = (int)min((i64)c.sms * 8, (total + 255) / 256);
-        if (c.world == 1) gather_rows(A, lda, n, Irow.p, k, R, ldr);
+        if (c.world == 1) gather_rows(A, lda, n, Irow, k, R, ldr);
         else {
             DBuf t((size_t)k * n);
-            gather_rows_owned_kernel<<<max(blocks, 1), 256, 0, c.stream>>>(A, lda, m, n, c.row0, Irow.p, k, t.p, k);
+            gather_rows_owned_kernel<<<max(blocks, 1), 256, 0, c.stream>>>(A, lda, m, n, c.row0, Irow, k, t.p, k);
             count_launch();
             allreduce_sum(t.p, (size_t)k * n);
             copy_matrix(t.p, k, R, ldr, k, n);
         }
     }
-    gather_cols(A, lda, m, Icol.p, k, Cm, ldc);                                      // C = M(:, Icol(1:k)) (RRA:2236-2237)
+    gather_cols(A, lda, m, Icol, k, Cm, ldc);                                        // C = M(:, Icol(1:k)) (RRA:2236-2237)
     DBuf RRt((size_t)k * k), RV((size_t)k * k), Rt((size_t)n * k);
     transpose(R, ldr, Rt.p, n, k, n);
     mm('T', 'N', k, k, n, 1.0, Rt.p, n, Rt.p, n, 0.0, RRt.p, k);                     // R R^T (RRA:2247)
@@ -391,6 +409,36 @@ int cur_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s,
     int info = lu_solve(RRt.p, k, k, RV.p, k, k);                                    // (R R^T) U^T = R V (RRA:2250)
     if (info) set_error("rsvd_b200: CUR core solve hit a zero pivot at column %d", info);
     transpose(RV.p, k, U, ldu, k, k);                                                // U = (U^T)^T (RRA:2252)
+    return g_status;
+}
+
+int cur_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed,
+             double *Cm, i64 ldc, double *U, i64 ldu, double *R, i64 ldr, i64 m_global) {
+    ensure_init();
+    if (!ctx().inited) return 1;
+    DBuf Icol((size_t)n), Irow((size_t)m_global), T((size_t)k * max((i64)1, n - k)), S((size_t)k * max((i64)1, m_global - k));
+    if (id_two_sided_rand(A, m, n, lda, k, p, q, s, seed, Icol.p, Irow.p, T.p, k, S.p, k, m_global)) return 1;   // RRA:2198
+    S.release();
+    return cur_from_id(A, m, n, lda, Icol.p, Irow.p, T.p, k, k, Cm, ldc, U, ldu, R, ldr);
+}
+
+// low_rank_svd_rand_decomp_fromQB (oneapi_code/rank_revealing_algorithms_one_api.c:244-304, restated in FP64):
+// B B^T = Uhat S^2 Uhat^T (descending), U = Q Uhat, V = B^T Uhat S^{-1}; all l = rows(B) triplets are returned.
+int svd_from_qb(const double *Q, i64 m, i64 ldq, const double *B, i64 l, i64 n, i64 ldb, double *U, i64 ldu, double *S,
+                double *V, i64 ldv) {
+    ensure_init();
+    Ctx &c = ctx();
+    if (!c.inited) return 1;
+    DBuf Bt((size_t)n * l), BBt((size_t)l * l), Uhat((size_t)l * l), Vt((size_t)l * l), X((size_t)l * l);
+    transpose(B, ldb, Bt.p, n, l, n);
+    mm('T', 'N', l, l, n, 1.0, Bt.p, n, Bt.p, n, 0.0, BBt.p, l);                     // B B^T (:262)
+    jacobi_svd(BBt.p, l, l, Uhat.p, l, S, Vt.p, l);                                  // :268
+    sqrt_clamp_kernel<<<(unsigned)((l + 127) / 128), 128, 0, c.stream>>>(S, (int)l); // :277-280
+    count_launch();
+    mm('N', 'N', m, l, l, 1.0, Q, ldq, Uhat.p, l, 0.0, U, ldu);                      // U = Q Uhat (:286)
+    copy_matrix(Uhat.p, l, X.p, l, l, l);
+    scale_cols(X.p, l, l, l, S, 1);                                                  // Uhat S^{-1} (:293-295)
+    mm('N', 'N', n, l, l, 1.0, Bt.p, n, X.p, l, 0.0, V, ldv);                        // V = B^T Uhat S^{-1} (:296)
     return g_status;
 }
 

@@ -295,6 +295,125 @@ void cur_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t q, idx_t s, mat 
     rsvd_api_sync_error();
 }
 
+/* ---- block-randomized ID / two-sided ID / CUR (RRA:1969-2027, 2086-2111, 2262-2332): consumers of the device QB ------------
+ * Column ID of the small factor B (pivoted QR on the device), then — for the two-sided and CUR variants — the same row-ID and
+ * CUR tails as the non-blocked routines, on the ORIGINAL M (re-uploaded over the QB residual). */
+static int blockrand_column_id(mat *M, idx_t k, idx_t p, double TOL, idx_t kstep, idx_t q, idx_t s, idx_t *frank,
+                               double **dA_out, double **dI_out, double **dT_out) {
+    idx_t n = M->ncols;
+    idx_t nstep = (kstep > 0) ? (k + p) / kstep : 0;          /* RRA:1974 (integer division) */
+    int rankMode = k > 0;
+    if (!rankMode) nstep = 0;                                 /* RRA:1980-1983 */
+    idx_t cap = 0, fr = 0;
+    double *dA = NULL, *dQ = NULL, *dB = NULL;
+    *dA_out = NULL; *dI_out = NULL; *dT_out = NULL;
+    if (randqb_device(M, kstep, nstep, TOL, q, s, &fr, &dA, &dQ, &dB, &cap)) {
+        rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dQ); rsvd_b200_dev_free(dB);
+        return 1;
+    }
+    rsvd_b200_dev_free(dQ);
+    idx_t rows = (nstep <= 0) ? fr : cap;                     /* B is cut to frank rows only in tolerance mode (RRA:1782-1789) */
+    if (rankMode) *frank = k;                                 /* RRA:2001-2002 */
+    else *frank = (idx_t)round(((double)fr / ((double)fr + (double)p + 1e-6)) * (double)fr);   /* RRA:2005 */
+    idx_t kk = *frank;
+    if (kk <= 0 || kk > rows || kk > n) {
+        rsvd_api_error("id_blockrand: rank %lld exceeds the %lld rows of B (the reference reads out of bounds here, SURVEY Q7)", (long long)kk, (long long)rows);
+        rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dB);
+        return 1;
+    }
+    double *dI = rsvd_b200_dev_alloc(n + 1), *dT = rsvd_b200_dev_alloc((rsvd_i64)kk * (n - kk) + 1);
+    if (dI && dT) rsvd_b200_id_qr_dev(dB, rows, n, cap, kk, dI, dT, kk);     /* pivotedQR_mkl(B) + T = Rk1^{-1} Rk2 (RRA:1996-2020) */
+    rsvd_b200_dev_free(dB);
+    *dA_out = dA; *dI_out = dI; *dT_out = dT;
+    rsvd_api_sync_error();
+    return g_api_status;
+}
+
+void id_blockrand_decomp_fixed_rank_or_prec(mat *M, idx_t k, idx_t p, double TOL, idx_t kstep, idx_t q, idx_t s, idx_t *frank, vec **I, mat **T) {
+    rsvd_api_begin();
+    idx_t n = M->ncols;
+    double *dA = NULL, *dI = NULL, *dT = NULL;
+    *I = NULL; *T = NULL;
+    if (blockrand_column_id(M, k, p, TOL, kstep, q, s, frank, &dA, &dI, &dT)) { *I = vector_new(n); *T = matrix_new(0, n); rsvd_b200_dev_free(dA); return; }
+    rsvd_b200_dev_free(dA);
+    *I = download_vec(dI, n);
+    *T = download_mat(dT, *frank, n - *frank);
+    rsvd_b200_dev_free(dI); rsvd_b200_dev_free(dT);
+    rsvd_api_sync_error();
+}
+
+void id_two_sided_blockrand_decomp_fixed_rank_or_prec(mat *M, idx_t k, idx_t p, double TOL, idx_t kstep, idx_t q, idx_t s, idx_t *frank,
+                                                      vec **Icol, vec **Irow, mat **T, mat **S) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols;
+    double *dA = NULL, *dI = NULL, *dT = NULL;
+    *Icol = NULL; *Irow = NULL; *T = NULL; *S = NULL;
+    if (blockrand_column_id(M, k, p, TOL, kstep, q, s, frank, &dA, &dI, &dT)) {
+        *Icol = vector_new(n); *Irow = vector_new(m); *T = matrix_new(0, n); *S = matrix_new(0, m); rsvd_b200_dev_free(dA); return;
+    }
+    idx_t kk = *frank;
+    if (rsvd_b200_h2d(dA, M->d, (rsvd_i64)m * n)) rsvd_api_sync_error();     /* the original M replaces the QB residual */
+    double *dIr = rsvd_b200_dev_alloc(m + 1), *dS = rsvd_b200_dev_alloc((rsvd_i64)kk * (m - kk) + 1);
+    if (dIr && dS) rsvd_b200_id_rows_dev(dA, m, n, m, dI, kk, dIr, dS, kk);  /* RRA:2098-2107 */
+    rsvd_b200_dev_free(dA);
+    *Icol = download_vec(dI, n); *Irow = download_vec(dIr, m);
+    *T = download_mat(dT, kk, n - kk); *S = download_mat(dS, kk, m - kk);
+    rsvd_b200_dev_free(dI); rsvd_b200_dev_free(dIr); rsvd_b200_dev_free(dT); rsvd_b200_dev_free(dS);
+    rsvd_api_sync_error();
+}
+
+void cur_blockrand_decomp_fixed_rank_or_prec(mat *M, idx_t k, idx_t p, double TOL, idx_t kstep, idx_t q, idx_t s, idx_t *frank,
+                                             mat **C, mat **U, mat **R) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols;
+    double *dA = NULL, *dI = NULL, *dT = NULL;
+    *C = NULL; *U = NULL; *R = NULL;
+    if (blockrand_column_id(M, k, p, TOL, kstep, q, s, frank, &dA, &dI, &dT)) {
+        *C = matrix_new(m, 0); *U = matrix_new(0, 0); *R = matrix_new(0, n); rsvd_b200_dev_free(dA); return;
+    }
+    idx_t kk = *frank;                                                       /* RRA:2272 */
+    if (rsvd_b200_h2d(dA, M->d, (rsvd_i64)m * n)) rsvd_api_sync_error();
+    double *dIr = rsvd_b200_dev_alloc(m + 1), *dS = rsvd_b200_dev_alloc((rsvd_i64)kk * (m - kk) + 1);
+    if (dIr && dS) rsvd_b200_id_rows_dev(dA, m, n, m, dI, kk, dIr, dS, kk);
+    rsvd_b200_dev_free(dS);
+    double *dC = rsvd_b200_dev_alloc((rsvd_i64)m * kk + 1), *dU = rsvd_b200_dev_alloc((rsvd_i64)kk * kk + 1), *dR = rsvd_b200_dev_alloc((rsvd_i64)kk * n + 1);
+    if (dIr && dC && dU && dR) rsvd_b200_cur_from_id_dev(dA, m, n, m, dI, dIr, dT, kk, kk, dC, m, dU, kk, dR, kk);   /* RRA:2274-2326 */
+    rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dI); rsvd_b200_dev_free(dIr); rsvd_b200_dev_free(dT);
+    *C = download_mat(dC, m, kk); *U = download_mat(dU, kk, kk); *R = download_mat(dR, kk, n);
+    rsvd_b200_dev_free(dC); rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dR);
+    rsvd_api_sync_error();
+}
+
+/* ---- SVD / ID from an existing QB (oneapi_code/rank_revealing_algorithms_one_api.c:244-304, 421-444, in FP64) ---------------- */
+void low_rank_svd_rand_decomp_fromQB(mat *Q, mat *B, mat **U, mat **S, mat **V) {
+    rsvd_api_begin();
+    idx_t m = Q->nrows, l = Q->ncols, n = B->ncols;
+    *U = NULL; *S = NULL; *V = NULL;
+    if (B->nrows != l) { rsvd_api_error("low_rank_svd_rand_decomp_fromQB: Q is %lld x %lld but B has %lld rows", (long long)m, (long long)l, (long long)B->nrows);
+                         *U = matrix_new(m, l); *S = matrix_new(l, l); *V = matrix_new(n, l); return; }
+    double *dQ = rsvd_upload(Q->d, (size_t)m * l), *dB = rsvd_upload(B->d, (size_t)l * n);
+    double *dU = rsvd_b200_dev_alloc((rsvd_i64)m * l + 1), *dS = rsvd_b200_dev_alloc(l + 1), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * l + 1);
+    if (dQ && dB && dU && dS && dV) rsvd_b200_svd_from_qb_dev(dQ, m, m, dB, l, n, l, dU, m, dS, dV, n);
+    rsvd_b200_dev_free(dQ); rsvd_b200_dev_free(dB);
+    *U = download_mat(dU, m, l); *S = diag_from_device(dS, l); *V = download_mat(dV, n, l);
+    rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dS); rsvd_b200_dev_free(dV);
+    rsvd_api_sync_error();
+}
+
+void id_rand_decomp_fromQB(mat *Q, mat *B, vec **I, mat **T) {
+    rsvd_api_begin();
+    idx_t l = B->nrows, n = B->ncols, k = Q->ncols;              /* k = Q->ncols (:429) */
+    *I = NULL; *T = NULL;
+    if (k <= 0 || k > l || k > n) { rsvd_api_error("id_rand_decomp_fromQB: need 0 < cols(Q) <= rows(B) <= cols(B)"); *I = vector_new(n); *T = matrix_new(0, n); return; }
+    double *dB = rsvd_upload(B->d, (size_t)l * n);
+    double *dI = rsvd_b200_dev_alloc(n + 1), *dT = rsvd_b200_dev_alloc((rsvd_i64)k * (n - k) + 1);
+    if (dB && dI && dT) rsvd_b200_id_qr_dev(dB, l, n, l, k, dI, dT, k);
+    rsvd_b200_dev_free(dB);
+    *I = download_vec(dI, n); *T = download_mat(dT, k, n - k);
+    rsvd_b200_dev_free(dI); rsvd_b200_dev_free(dT);
+    rsvd_api_sync_error();
+}
+
 /* ---- evaluation helpers (RRA:2337-2573): 100*||M - approx||_F/||M||_F, printed like the reference ------------------- */
 void use_low_rank_svd_for_approximation(mat *M, mat *U, mat *S, mat *V) {
     rsvd_api_begin();

@@ -59,6 +59,10 @@ SIGNATURES = {
     "rsvd_b200_svd_from_q_dev": (C.c_int, [dp, i64, i64, i64, dp, i64, i64, i64, C.c_int, dp, i64, dp, dp, i64]),
     "rsvd_b200_id_rand_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, dp, dp, dp, i64]),
     "rsvd_b200_id_full_dev": (C.c_int, [dp, i64, i64, i64, dp, dp, i64]),
+    "rsvd_b200_id_qr_dev": (C.c_int, [dp, i64, i64, i64, i64, dp, dp, i64]),
+    "rsvd_b200_id_rows_dev": (C.c_int, [dp, i64, i64, i64, dp, i64, dp, dp, i64]),
+    "rsvd_b200_cur_from_id_dev": (C.c_int, [dp, i64, i64, i64, dp, dp, dp, i64, i64, dp, i64, dp, i64, dp, i64]),
+    "rsvd_b200_svd_from_qb_dev": (C.c_int, [dp, i64, i64, dp, i64, i64, i64, dp, i64, dp, dp, i64]),
     "rsvd_b200_id_two_sided_rand_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, dp, dp, dp, i64, dp, i64]),
     "rsvd_b200_cur_rand_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, dp, i64, dp, i64, dp, i64]),
     "rsvd_b200_svd_percent_error_dev": (C.c_double, [dp, i64, i64, i64, dp, i64, dp, dp, i64, i64]),

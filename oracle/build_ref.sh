@@ -27,7 +27,7 @@ if [ -d "$REF/multi_core_mkl_code" ]; then
   PKG="$HERE/../lowrankmatrixdecompositioncodes_b200"
   if [ -f "$PKG/librsvd_b200_api32.so" ]; then
     mkdir -p "$OUT/relink"; TMP="$(mktemp -d)"
-    for d in driver_multi_core_mkl1 driver_multi_core_mkl5; do
+    for d in driver_multi_core_mkl1 driver_multi_core_mkl3 driver_multi_core_mkl5; do
       cp "$D32/$d.c" "$TMP/$d.c"
       gcc -O2 -w -I"$HERE/../include" "$TMP/$d.c" -L"$PKG" -lrsvd_b200_api32 -lrsvd_b200 -lm -Wl,-rpath,'$ORIGIN/../../../lowrankmatrixdecompositioncodes_b200' -o "$OUT/relink/$d"
     done

@@ -52,6 +52,9 @@ class RefLib:
         L.id_rand_decomp_fixed_rank.argtypes = [PM, I, I, I, I, PPV, PPM]
         L.id_two_sided_rand_decomp_fixed_rank.argtypes = [PM, I, I, I, I, PPV, PPV, PPM, PPM]
         L.cur_rand_decomp_fixed_rank.argtypes = [PM, I, I, I, I, PPM, PPM, PPM]
+        L.id_blockrand_decomp_fixed_rank_or_prec.argtypes = [PM, I, I, C.c_double, I, I, I, C.POINTER(I), PPV, PPM]
+        L.id_two_sided_blockrand_decomp_fixed_rank_or_prec.argtypes = [PM, I, I, C.c_double, I, I, I, C.POINTER(I), PPV, PPV, PPM, PPM]
+        L.cur_blockrand_decomp_fixed_rank_or_prec.argtypes = [PM, I, I, C.c_double, I, I, I, C.POINTER(I), PPM, PPM, PPM]
         L.matrix_load_from_binary_file.restype = PM
         L.matrix_load_from_binary_file.argtypes = [C.c_char_p]
         L.matrix_write_to_binary_file.argtypes = [PM, C.c_char_p]
@@ -150,6 +153,37 @@ class RefLib:
         self.lib.cur_rand_decomp_fixed_rank(M, k, p, q, s, C.byref(Cm), C.byref(U), C.byref(R))
         self.lib.matrix_delete(M)
         return self.from_mat(Cm), self.from_mat(U), self.from_mat(R)
+
+
+    def id_blockrand(self, A, k, p, TOL, kstep, q, s, seed=777):
+        self.set_seed(seed)
+        M = self.to_mat(A)
+        I_, T = C.POINTER(self.Vec)(), C.POINTER(self.Mat)()
+        frank = self.I(0)
+        self.lib.id_blockrand_decomp_fixed_rank_or_prec(M, k, p, float(TOL), kstep, q, s, C.byref(frank), C.byref(I_), C.byref(T))
+        self.lib.matrix_delete(M)
+        return int(frank.value), self.from_vec(I_), self.from_mat(T)
+
+    def id_two_sided_blockrand(self, A, k, p, TOL, kstep, q, s, seed=777):
+        self.set_seed(seed)
+        M = self.to_mat(A)
+        PV, PM = C.POINTER(self.Vec), C.POINTER(self.Mat)
+        Ic, Ir, T, S = PV(), PV(), PM(), PM()
+        frank = self.I(0)
+        self.lib.id_two_sided_blockrand_decomp_fixed_rank_or_prec(M, k, p, float(TOL), kstep, q, s, C.byref(frank), C.byref(Ic), C.byref(Ir),
+                                                                  C.byref(T), C.byref(S))
+        self.lib.matrix_delete(M)
+        return int(frank.value), self.from_vec(Ic), self.from_vec(Ir), self.from_mat(T), self.from_mat(S)
+
+    def cur_blockrand(self, A, k, p, TOL, kstep, q, s, seed=777):
+        self.set_seed(seed)
+        M = self.to_mat(A)
+        PM = C.POINTER(self.Mat)
+        Cm, U, R = PM(), PM(), PM()
+        frank = self.I(0)
+        self.lib.cur_blockrand_decomp_fixed_rank_or_prec(M, k, p, float(TOL), kstep, q, s, C.byref(frank), C.byref(Cm), C.byref(U), C.byref(R))
+        self.lib.matrix_delete(M)
+        return int(frank.value), self.from_mat(Cm), self.from_mat(U), self.from_mat(R)
 
     def omega(self, nrows, ncols, seed=777):
         """The Omega the reference would draw for an nrows x ncols initialize_random_matrix."""

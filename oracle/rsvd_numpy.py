@@ -253,6 +253,55 @@ def cur_rand_decomp_fixed_rank(M, k, p, q, s, seed=777):
     return Cm, Ut.T, R                                                      # RRA:2252
 
 
+def id_blockrand_decomp_fixed_rank_or_prec(M, k, p, TOL, kstep, q, s, seed=777):
+    """RRA:1969-2027 — column ID from the pivoted QR of the QB factor B."""
+    nstep = int((k + p) // kstep)                                           # RRA:1974
+    rankMode = k > 0
+    if not rankMode:
+        nstep = 0                                                           # RRA:1980-1983
+    frank, Q, B = randQB_pb_new(M, kstep, nstep, TOL, q, s, seed)           # RRA:1989
+    Rk, I = pivotedQR_mkl(B)                                                # RRA:1998
+    frank = k if rankMode else int(round((frank / (frank + p + 1e-6)) * frank))   # RRA:2001-2006
+    T = upper_triangular_system_solve(np.triu(Rk[:frank, :frank]), Rk[:frank, frank:])   # RRA:2009-2020
+    return frank, I, T
+
+
+def id_two_sided_blockrand_decomp_fixed_rank_or_prec(M, k, p, TOL, kstep, q, s, seed=777):
+    """RRA:2086-2111."""
+    frank, Icol, T = id_blockrand_decomp_fixed_rank_or_prec(M, k, p, TOL, kstep, q, s, seed)
+    MI = M[:, Icol[:frank].astype(np.int64)]
+    Irow, S = id_decomp_full(np.ascontiguousarray(MI.T), frank)
+    return frank, Icol, Irow, T, S
+
+
+def cur_blockrand_decomp_fixed_rank_or_prec(M, k, p, TOL, kstep, q, s, seed=777):
+    """RRA:2262-2332."""
+    frank, Icol, Irow, T, S = id_two_sided_blockrand_decomp_fixed_rank_or_prec(M, k, p, TOL, kstep, q, s, seed)
+    n = M.shape[1]
+    Icolinv = np.empty(n, dtype=np.int64)
+    Icolinv[Icol.astype(np.int64)] = np.arange(n)
+    V = np.vstack([np.eye(frank), T.T])[Icolinv, :]
+    R = M[Irow[:frank].astype(np.int64), :]
+    Cm = M[:, Icol[:frank].astype(np.int64)]
+    Ut = square_matrix_system_solve(R @ R.T, R @ V)
+    return frank, Cm, Ut.T, R
+
+
+def low_rank_svd_rand_decomp_fromQB(Q, B):
+    """oneapi_code/rank_revealing_algorithms_one_api.c:244-304, restated in FP64 (the reference ships it in float32 only):
+    SVD of B B^T (descending), S = sqrt, U = Q Uhat, V = B^T Uhat S^{-1}."""
+    Uhat, St, _ = singular_value_decomposition(B @ B.T)
+    sing = np.sqrt(np.diag(St))
+    return Q @ Uhat, np.diag(sing), B.T @ (Uhat / sing)
+
+
+def id_rand_decomp_fromQB(Q, B):
+    """oneapi_code/rank_revealing_algorithms_one_api.c:421-444 in FP64: pivoted QR of B, k = cols(Q)."""
+    k = Q.shape[1]
+    Rk, I = pivotedQR_mkl(B)
+    return I, upper_triangular_system_solve(np.triu(Rk[:k, :k]), Rk[:k, k:])
+
+
 # ------------------------------------------------------------------------------------------------
 # synthetic inputs + binary file formats
 # ------------------------------------------------------------------------------------------------

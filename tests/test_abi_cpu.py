@@ -140,7 +140,7 @@ def test_reference_drivers_relink_unchanged():
     d = os.path.join(ROOT, "oracle", "_ref", "relink")
     if not os.path.isdir(d):
         pytest.skip("relinked drivers not built (reference tree absent)")
-    for name in ["driver_multi_core_mkl1", "driver_multi_core_mkl5", "driver1_64bit"]:
+    for name in ["driver_multi_core_mkl1", "driver_multi_core_mkl3", "driver_multi_core_mkl5", "driver1_64bit"]:
         exe = os.path.join(d, name)
         assert os.path.exists(exe), name
         out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout

@@ -201,6 +201,47 @@ def test_id_two_sided_and_cur_vs_reference(api, oracle, m, n, k, p, q, s, spec):
     assert abs(e - er) <= 0.01 * er
 
 
+def test_blockrand_id_cur_vs_reference(api, oracle):
+    """id_blockrand / id_two_sided_blockrand / cur_blockrand (RRA:1969-2027, 2086-2111, 2262-2332),
+    driver_multi_core_mkl3.c's parameters scaled down (p = kstep)."""
+    A, _ = O.make_matrix(1200, 900, "logspace", seed=5)
+    k, kstep, q, s = 80, 20, 1, 2
+    ref = oracle if hasattr(oracle, "id_blockrand") else None
+    f, I, T = api.id_blockrand(A, k, kstep, 0.0, kstep, q, s, seed=3)
+    fr, Ir_, Tr = (ref.id_blockrand(A, k, kstep, 0.0, kstep, q, s, seed=3) if ref else O.id_blockrand_decomp_fixed_rank_or_prec(A, k, kstep, 0.0, kstep, q, s, 3))
+    assert f == fr == k and np.array_equal(I, Ir_) and np.abs(T - Tr).max() < 1e-10
+    f, Ic, Irow, T, S = api.id_two_sided_blockrand(A, k, kstep, 0.0, kstep, q, s, seed=3)
+    fr, Icr, Irr, Tr, Sr = (ref.id_two_sided_blockrand(A, k, kstep, 0.0, kstep, q, s, seed=3) if ref else
+                            O.id_two_sided_blockrand_decomp_fixed_rank_or_prec(A, k, kstep, 0.0, kstep, q, s, 3))
+    assert f == fr and np.array_equal(Ic, Icr) and np.array_equal(Irow, Irr) and np.abs(S - Sr).max() < 1e-10
+    f, Cm, U, R = api.cur_blockrand(A, k, kstep, 0.0, kstep, q, s, seed=3)
+    fr, Cr, Ur, Rr = (ref.cur_blockrand(A, k, kstep, 0.0, kstep, q, s, seed=3) if ref else
+                      O.cur_blockrand_decomp_fixed_rank_or_prec(A, k, kstep, 0.0, kstep, q, s, 3))
+    assert f == fr and np.array_equal(Cm, Cr) and np.array_equal(R, Rr)
+    e, er = O.get_percent_error_between_two_mats(A, Cm @ U @ R), O.get_percent_error_between_two_mats(A, Cr @ Ur @ Rr)
+    assert abs(e - er) <= 0.01 * er
+    # tolerance mode (k = 0): the QB loop stops on the device, frank = round(f/(f+p) f)  (SURVEY Q1: this entry point DOES honour TOL)
+    tol = 0.35 * np.linalg.norm(A)
+    f, I, T = api.id_blockrand(A, 0, kstep, tol, kstep, q, s, seed=3)
+    fr, Ir_, Tr = (ref.id_blockrand(A, 0, kstep, tol, kstep, q, s, seed=3) if ref else O.id_blockrand_decomp_fixed_rank_or_prec(A, 0, kstep, tol, kstep, q, s, 3))
+    assert f == fr and 0 < f < 900 and np.array_equal(I, Ir_) and np.abs(T - Tr).max() < 1e-10
+
+
+def test_svd_and_id_from_qb(api):
+    """low_rank_svd_rand_decomp_fromQB / id_rand_decomp_fromQB (oneapi_code/…one_api.c:244-304, 421-444) in FP64,
+    checked against the numpy restatement (the reference ships these in float32 only) and against the direct routines."""
+    A, sig = O.make_matrix(900, 700, "gap", seed=8, k=40, tail=1e-7)
+    f, Q, B = api.randQB_pb_new(A, 20, 3, 0.0, 2, 1, seed=5)
+    U, S, V = api.svd_from_qb(Q, B)
+    Ur, Sr, Vr = O.low_rank_svd_rand_decomp_fromQB(Q, B)
+    assert rel_sigma_err(np.diag(S)[:40], np.diag(Sr)[:40]) < 1e-7      # sigma^2 route: eps*(s1/sk)^2
+    assert rel_sigma_err(np.diag(S)[:40], sig[:40]) < 1e-6
+    assert np.linalg.norm(A - U[:, :40] @ S[:40, :40] @ V[:, :40].T) / np.linalg.norm(A) < 1e-6
+    I, T = api.id_from_qb(Q, B)
+    Ir, Tr = O.id_rand_decomp_fromQB(Q, B)
+    assert np.array_equal(I, Ir) and np.abs(T - Tr).max() < 1e-9
+
+
 def test_evaluation_helpers_print_reference_metric(api, capfd):
     A, _ = O.make_matrix(400, 300, "exp", seed=1)
     U, S, V = api.svd_rand(A, 20, 5, 1, 2, 1, seed=1)
