@@ -12,8 +12,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 8;       // 16 KB
 constexpr int B_STAGE_BYTES = BN_MAX * BK * 8;   // 16 KB
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int NTHREADS = 384;           // 1 producer + 2 consumer warpgroups
-constexpr int NTHREADS_PHILOX = 512;    // sketch mode: 2 producer warpgroups (TMA warp + two Omega generator groups) + 2 consumer warpgroups
-constexpr int GEN_T = 96;               // threads per Omega generator group
+constexpr int NTHREADS_PHILOX = 512;    // sketch mode: 2 producer warpgroups (alternate stages) + 2 consumer warpgroups
 constexpr int PART_TILE = BM * BN_MAX;           // doubles per partial tile
 
 struct TmaP {
@@ -109,7 +108,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), PHILOX ? GEN_T + 1 : 1);
+            mbar_init(full_bar(s), PHILOX ? 129 : 1);
             mbar_init(empty_bar(s), 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -119,94 +118,91 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     constexpr int NPWG = PHILOX ? 2 : 1;     // producer warpgroups
     if (warp < 4 * NPWG) {
         // ===================== producer warpgroup(s) =====================
-        if (PHILOX) asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        // sketch mode: generating one Omega tile costs ~1.3x the DMMA time of a stage for a single warpgroup (latency-
+        // bound Philox + Box-Muller chains), so two warpgroups take alternate stages.
+        if (PHILOX) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-        // TMA issue: one thread, free-running over all stages (plain mode: warp 0; sketch mode: the last producer warp, so
-        // that the A-tile prefetch distance does not depend on how far the Omega generators have got)
-        const bool tma_thread = PHILOX ? (warp == 4 * NPWG - 1 && lane == 0) : (tid == 0);
-        if (tma_thread) {
-            for (int it = 0; it < niter; ++it) {
+        const int pw = warp >> 2;                // which producer warpgroup
+        const int ptid = tid & 127;              // thread index inside it
+        if (PHILOX || tid == 0) {
+            for (int it = pw; it < niter; it += NPWG) {
                 const int s = it % STAGES;
                 const uint32_t ph = (uint32_t)((it / STAGES) & 1);
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 const int kc = (it0 + it) * BK;
-                const uint32_t fb = full_bar(s);
-                mbar_expect_tx(fb, PHILOX ? A_STAGE_BYTES : (A_STAGE_BYTES + b_bytes));
-                if (A_KMAJOR) {
-                    tma_load_2d(sA + s * A_STAGE_BYTES, &mapA, kc, (int)m0, fb);
-                } else {
+                if (ptid == 0) {
+                    const uint32_t fb = full_bar(s);
+                    mbar_expect_tx(fb, PHILOX ? A_STAGE_BYTES : (A_STAGE_BYTES + b_bytes));
+                    if (A_KMAJOR) {
+                        tma_load_2d(sA + s * A_STAGE_BYTES, &mapA, kc, (int)m0, fb);
+                    } else {
 #pragma unroll
-                    for (int b = 0; b < 8; ++b)
-                        tma_load_2d(sA + s * A_STAGE_BYTES + b * 2048, &mapA, (int)m0 + 16 * b, kc, fb);
+                        for (int b = 0; b < 8; ++b)
+                            tma_load_2d(sA + s * A_STAGE_BYTES + b * 2048, &mapA, (int)m0 + 16 * b, kc, fb);
+                    }
+                    if (!PHILOX) tma_load_2d(sB + s * B_STAGE_BYTES, &mapB, kc, (int)n0, fb);
                 }
-                if (!PHILOX) tma_load_2d(sB + s * B_STAGE_BYTES, &mapB, kc, (int)n0, fb);
-            }
-        }
-        // sketch mode: Omega generators.  Generating one tile costs more than the DMMA time of a stage for one group
-        // (latency-bound Philox + Box-Muller chains), so two groups of GEN_T threads (warps 0-2 and 4-6) take alternate stages.
-        if (PHILOX && (warp & 3) != 3) {
-            const int grp = warp >> 2;                       // 0 or 1
-            const int gtid = (warp & 3) * 32 + lane;         // 0 .. GEN_T-1
-            for (int it = grp; it < niter; it += 2) {
-                const int s = it % STAGES;
-                const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                const int kc = (it0 + it) * BK;
-                // Omega tile: element (col j, kk) = normal(seed, off + (kc+kk)*sk + (n0+j)*sc), written at bswz(j, kk)
-                // (the image a TMA SWIZZLE_128B load of a stored Omega would have produced).
-                const uint32_t bbase = sB + s * B_STAGE_BYTES;
-                constexpr int ncols = 8 * NB;
-                const i64 lin_tile = p.ph_off + (i64)kc * p.ph_sk + n0 * p.ph_sc;
-                if (p.ph_sk == 1 && ((lin_tile | p.ph_sc) & 3) == 0) {
-                    // linear index runs along k and every column starts on a Philox block: item = (column, k-quad)
-                    constexpr int nitems = ncols * 4;
-                    constexpr int ROUNDS = (nitems + GEN_T - 1) / GEN_T;
-                    float z[ROUNDS][4];
+                if (PHILOX) {
+                    // Omega tile: element (col j, kk) = normal(seed, off + (kc+kk)*sk + (n0+j)*sc), written at bswz(j, kk)
+                    // (the image a TMA SWIZZLE_128B load of a stored Omega would have produced).
+                    const uint32_t bbase = sB + s * B_STAGE_BYTES;
+                    constexpr int ncols = 8 * NB;
+                    if (p.ph_sk == 1) {
+                        // linear index runs along k: thread = column, its 16 entries are 4 aligned Philox blocks
+                        const int j = ptid;
+                        if (j < ncols) {
+                            const uint64_t lin0 = (uint64_t)(p.ph_off + (i64)kc + (n0 + j) * p.ph_sc);
+                            if ((lin0 & 3u) == 0) {
+                                float z[4][4];
 #pragma unroll
-                    for (int r = 0; r < ROUNDS; ++r) {
-                        const int item = gtid + r * GEN_T;
-                        if (item < nitems) {
-                            const int j = item % ncols, qd = item / ncols;
-                            rsvd_normal4(p.seed, (uint64_t)((lin_tile + j * p.ph_sc) >> 2) + qd, z[r]);   // independent chains
+                                for (int qd = 0; qd < 4; ++qd) rsvd_normal4(p.seed, (lin0 >> 2) + qd, z[qd]);   // 4 independent chains
+#pragma unroll
+                                for (int qd = 0; qd < 4; ++qd) {
+                                    sts128(bbase + j * 128 + (((2 * qd) ^ (j & 7)) << 4), (double)z[qd][0], (double)z[qd][1]);
+                                    sts128(bbase + j * 128 + (((2 * qd + 1) ^ (j & 7)) << 4), (double)z[qd][2], (double)z[qd][3]);
+                                }
+                            } else {
+                                uint64_t cached = ~0ull;
+                                float z[4];
+                                for (int kk = 0; kk < 16; ++kk) {
+                                    uint64_t lin = lin0 + (uint64_t)kk;
+                                    if ((lin >> 2) != cached) { cached = lin >> 2; rsvd_normal4(p.seed, cached, z); }
+                                    uint32_t sel = (uint32_t)lin & 3u;
+                                    float f = sel == 0 ? z[0] : (sel == 1 ? z[1] : (sel == 2 ? z[2] : z[3]));
+                                    sts64(bbase + bswz(j, kk), (double)f);
+                                }
+                            }
+                        }
+                    } else if (p.ph_sc == 1 && ((p.ph_sk | (p.ph_off + n0)) & 3) == 0) {
+                        // linear index runs along the columns (left sketch of the ID): item = (k, column quad)
+                        constexpr int nitems = 16 * 2 * NB;    // 16 k  x  ncols/4 quads
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int item = ptid + r * 128;
+                            if (item < nitems) {
+                                const int kk = item & 15, cq = item >> 4;
+                                const uint64_t lin = (uint64_t)(p.ph_off + ((i64)kc + kk) * p.ph_sk + n0 + 4 * cq);
+                                float z[4];
+                                rsvd_normal4(p.seed, lin >> 2, z);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) sts64(bbase + bswz(4 * cq + i, kk), (double)z[i]);
+                            }
+                        }
+                    } else {
+                        // arbitrary strides: one Philox block per element
+                        for (int e = ptid; e < ncols * 16; e += 128) {
+                            const int kk = e & 15, j = e >> 4;
+                            const uint64_t lin = (uint64_t)(p.ph_off + ((i64)kc + kk) * p.ph_sk + (n0 + j) * p.ph_sc);
+                            sts64(bbase + bswz(j, kk), (double)rsvd_normal_at(p.seed, lin));
                         }
                     }
-#pragma unroll
-                    for (int r = 0; r < ROUNDS; ++r) {
-                        const int item = gtid + r * GEN_T;
-                        if (item < nitems) {
-                            const int j = item % ncols, qd = item / ncols;
-                            sts128(bbase + j * 128 + (((2 * qd) ^ (j & 7)) << 4), (double)z[r][0], (double)z[r][1]);
-                            sts128(bbase + j * 128 + (((2 * qd + 1) ^ (j & 7)) << 4), (double)z[r][2], (double)z[r][3]);
-                        }
-                    }
-                } else if (p.ph_sc == 1 && ((lin_tile | p.ph_sk) & 3) == 0) {
-                    // linear index runs along the columns (left sketch of the ID): item = (k, column quad)
-                    constexpr int nitems = 16 * 2 * NB;    // 16 k  x  ncols/4 quads
-                    constexpr int ROUNDS = (nitems + GEN_T - 1) / GEN_T;
-#pragma unroll
-                    for (int r = 0; r < ROUNDS; ++r) {
-                        const int item = gtid + r * GEN_T;
-                        if (item < nitems) {
-                            const int kk = item & 15, cq = item >> 4;
-                            float z[4];
-                            rsvd_normal4(p.seed, (uint64_t)((lin_tile + (i64)kk * p.ph_sk + 4 * cq) >> 2), z);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) sts64(bbase + bswz(4 * cq + i, kk), (double)z[i]);
-                        }
-                    }
-                } else {
-                    // arbitrary strides / alignment: one Philox block per element
-                    for (int e = gtid; e < ncols * 16; e += GEN_T) {
-                        const int kk = e & 15, j = e >> 4;
-                        sts64(bbase + bswz(j, kk), (double)rsvd_normal_at(p.seed, (uint64_t)(lin_tile + (i64)kk * p.ph_sk + j * p.ph_sc)));
-                    }
+                    mbar_arrive(full_bar(s));
                 }
-                mbar_arrive(full_bar(s));
             }
         }
     } else {
         // ===================== consumer warpgroups =====================
-        if (PHILOX) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        if (PHILOX) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         const int cw = warp - 4 * NPWG;           // rows [16*cw, 16*cw+16) of the tile, all columns
         const int g = lane >> 2, t = lane & 3;

@@ -7,10 +7,9 @@
 // registers, forms the 2x2 Gram entries with a block reduction and rotates the columns of G and of the
 // accumulated V.  The l x l working set (<= 2 x 8.8 MB at l = 1050) stays L2-resident.
 // The whole iteration (all steps of all sweeps, convergence test included) is ONE persistent cooperative kernel: the
-// N/2 CTAs are co-resident and order their steps through per-column version counters in L2 (a CTA waits only for the
-// two CTAs that last touched its columns), with one device-wide barrier per sweep for the convergence vote, instead of
-// one kernel launch per step (519 steps x 9 sweeps at l = 520).  A graph-replayed per-step kernel remains as the
-// fallback when the grid cannot be co-resident.
+// N/2 CTAs are co-resident and separate the steps with a device-wide barrier (an atomic counter in L2, ~1 us) instead
+// of one kernel launch per step (~4.3 us in a CUDA graph: 519 steps x 9 sweeps at l = 520).  A graph-replayed
+// per-step kernel remains as the fallback when the grid cannot be co-resident.
 #include "common.cuh"
 #include <algorithm>
 #include <vector>
@@ -105,53 +104,33 @@ __device__ __forceinline__ bool grid_barrier(int *bar, int gen, int *err) {
     return ok_s != 0;
 }
 
-// ctl[0] = barrier counter, ctl[1] = error flag, ctl[2] = sweeps done, ctl[8 + s] = CTAs that rotated in sweep s,
-// ctl[64 + c] = version of column c (number of steps applied to it).
-// Steps are ordered by point-to-point dependencies instead of a device-wide barrier: the CTA that owns pair (p,q) at global
-// step g only waits until the two CTAs that touched p and q at step g-1 have published ver[p] = ver[q] = g.  One
-// device-wide barrier per sweep remains for the convergence vote.
+// ctl[0] = barrier counter, ctl[1] = error flag, ctl[2] = sweeps done, ctl[8 + s] = CTAs that rotated in sweep s
 __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ldg, double *V, i64 ldv, int n, int N, double tol,
                                                                int max_sweeps, int *ctl) {
     __shared__ double sh[3 * (JT / 32)];
-    __shared__ int ok_s;
     const int i = blockIdx.x;
-    int *ver = ctl + 64;
-    int gen = 0, gs = 0;
+    int gen = 0;
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
         int rotated = 0;
-        for (int r = 0; r < N - 1; ++r, ++gs) {
+        for (int r = 0; r < N - 1; ++r) {
             int p, q;
             if (i == 0) { p = N - 1; q = r; }
             else { p = (r + i) % (N - 1); q = (r - i + (N - 1)) % (N - 1); }
             if (p > q) { int t = p; p = q; q = t; }
-            // wait for both columns to be at version gs
-            if (threadIdx.x == 0) {
-                int ok = 1;
-                long long spins = 0;
-                while (*((volatile int *)(ver + p)) < gs || *((volatile int *)(ver + q)) < gs) {
-                    if (++spins > (1ll << 26) || *((volatile int *)(ctl + 1))) { ok = 0; ctl[1] = 1; break; }
-                }
-                __threadfence();
-                ok_s = ok;
-            }
-            __syncthreads();
-            if (!ok_s) return;
             if (q < n) {
                 double *gp = G + (i64)p * ldg, *gq = G + (i64)q * ldg;
-                double *vp = V + (i64)p * ldv, *vq = V + (i64)q * ldv;
-                double xp[JR], xq[JR], yp[JR], yq[JR];
+                double xp[JR], xq[JR];
                 double a = 0.0, b = 0.0, c = 0.0;
 #pragma unroll
                 for (int k = 0; k < JR; ++k) {
                     int row = threadIdx.x + k * JT;
                     xp[k] = row < n ? __ldcg(gp + row) : 0.0;     // L2 loads: other SMs wrote these columns in the previous step
                     xq[k] = row < n ? __ldcg(gq + row) : 0.0;
-                    yp[k] = row < n ? __ldcg(vp + row) : 0.0;     // V columns fetched up front: off the critical path
-                    yq[k] = row < n ? __ldcg(vq + row) : 0.0;
                     a = fma(xp[k], xp[k], a);
                     b = fma(xq[k], xq[k], b);
                     c = fma(xp[k], xq[k], c);
                 }
+                __syncthreads();     // sh reuse across steps
                 block_sum3(a, b, c, sh);
                 if (fabs(c) > tol * sqrt(a * b) && a != 0.0 && b != 0.0) {
                     const double zeta = (b - a) / (2.0 * c);
@@ -164,21 +143,23 @@ __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ld
                         if (row < n) {
                             gp[row] = cs * xp[k] - sn * xq[k];
                             gq[row] = sn * xp[k] + cs * xq[k];
-                            vp[row] = cs * yp[k] - sn * yq[k];
-                            vq[row] = sn * yp[k] + cs * yq[k];
+                        }
+                    }
+                    double *vp = V + (i64)p * ldv, *vq = V + (i64)q * ldv;
+#pragma unroll
+                    for (int k = 0; k < JR; ++k) {
+                        int row = threadIdx.x + k * JT;
+                        if (row < n) {
+                            double y = __ldcg(vp + row), z = __ldcg(vq + row);
+                            vp[row] = cs * y - sn * z;
+                            vq[row] = sn * y + cs * z;
                         }
                     }
                 }
             }
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                *((volatile int *)(ver + p)) = gs + 1;
-                *((volatile int *)(ver + q)) = gs + 1;
-            }
+            if (r == N - 2 && rotated && threadIdx.x == 0) atomicAdd(ctl + 8 + sweep, 1);
+            if (!grid_barrier(ctl, gen++, ctl + 1)) return;
         }
-        if (rotated && threadIdx.x == 0) atomicAdd(ctl + 8 + sweep, 1);
-        if (!grid_barrier(ctl, gen++, ctl + 1)) return;
         const int nrot = *((volatile int *)(ctl + 8 + sweep));
         if (blockIdx.x == 0 && threadIdx.x == 0) ctl[2] = sweep + 1;
         if (nrot == 0) break;
@@ -228,8 +209,8 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
         RSVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_persistent_kernel, JT, 0));
     }
     if (coop > 0 && N / 2 <= blocks_per_sm * c.sms && !getenv("RSVD_B200_JACOBI_GRAPH")) {
-        int *ctl = (int *)dalloc_bytes((size_t)(64 + N) * sizeof(int));
-        RSVD_CUDA(cudaMemsetAsync(ctl, 0, (size_t)(64 + N) * sizeof(int), c.stream));
+        int *ctl = (int *)dalloc_bytes(64 * sizeof(int));
+        RSVD_CUDA(cudaMemsetAsync(ctl, 0, 64 * sizeof(int), c.stream));
         int ms = max_sweeps;
         void *args[] = {&G, &ldg, &V, &ldv, (void *)&n, (void *)&N, (void *)&tol, &ms, &ctl};
         cudaError_t e = cudaLaunchCooperativeKernel((void *)jacobi_persistent_kernel, dim3(N / 2), dim3(JT), args, 0, c.stream);
