@@ -69,19 +69,6 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// float -> double widening with integer instructions only.  F2F.F64.F32 executes on the FP64 pipe that the consumer warps'
-// DMMAs saturate (ncu: the 16 conversions per generator thread and stage cost the sketch kernel ~12 % of DMMA throughput);
-// the exact widening is a 3-bit exponent re-bias and a mantissa shift.  Zero and (never produced here) denormals take the
-// generic conversion.
-__device__ __forceinline__ double widen(float f) {
-    const uint32_t b = __float_as_uint(f);
-    const uint32_t mag = b & 0x7fffffffu;
-    if (mag < 0x00800000u) return (double)f;            // +-0 or denormal: rare, exact fallback
-    const uint32_t hi = (b & 0x80000000u) | ((mag >> 3) + 0x38000000u);
-    const uint32_t lo = mag << 29;
-    return __hiloint2double((int)hi, (int)lo);
-}
-
 // byte offset of element (column j, k index kk) inside a K-major [col][16 k] stage under SWIZZLE_128B
 __device__ __forceinline__ uint32_t bswz(int j, int kk) {
     return (uint32_t)(j * 128 + ((((kk >> 1) ^ (j & 7))) << 4) + (kk & 1) * 8);
@@ -171,8 +158,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                 for (int qd = 0; qd < 4; ++qd) rsvd_normal4(p.seed, (lin0 >> 2) + qd, z[qd]);   // 4 independent chains
 #pragma unroll
                                 for (int qd = 0; qd < 4; ++qd) {
-                                    sts128(bbase + j * 128 + (((2 * qd) ^ (j & 7)) << 4), widen(z[qd][0]), widen(z[qd][1]));
-                                    sts128(bbase + j * 128 + (((2 * qd + 1) ^ (j & 7)) << 4), widen(z[qd][2]), widen(z[qd][3]));
+                                    sts128(bbase + j * 128 + (((2 * qd) ^ (j & 7)) << 4), (double)z[qd][0], (double)z[qd][1]);
+                                    sts128(bbase + j * 128 + (((2 * qd + 1) ^ (j & 7)) << 4), (double)z[qd][2], (double)z[qd][3]);
                                 }
                             } else {
                                 uint64_t cached = ~0ull;
@@ -182,7 +169,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                     if ((lin >> 2) != cached) { cached = lin >> 2; rsvd_normal4(p.seed, cached, z); }
                                     uint32_t sel = (uint32_t)lin & 3u;
                                     float f = sel == 0 ? z[0] : (sel == 1 ? z[1] : (sel == 2 ? z[2] : z[3]));
-                                    sts64(bbase + bswz(j, kk), widen(f));
+                                    sts64(bbase + bswz(j, kk), (double)f);
                                 }
                             }
                         }
@@ -198,7 +185,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                 float z[4];
                                 rsvd_normal4(p.seed, lin >> 2, z);
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) sts64(bbase + bswz(4 * cq + i, kk), widen(z[i]));
+                                for (int i = 0; i < 4; ++i) sts64(bbase + bswz(4 * cq + i, kk), (double)z[i]);
                             }
                         }
                     } else {
@@ -206,7 +193,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         for (int e = ptid; e < ncols * 16; e += 128) {
                             const int kk = e & 15, j = e >> 4;
                             const uint64_t lin = (uint64_t)(p.ph_off + ((i64)kc + kk) * p.ph_sk + (n0 + j) * p.ph_sc);
-                            sts64(bbase + bswz(j, kk), widen(rsvd_normal_at(p.seed, lin)));
+                            sts64(bbase + bswz(j, kk), (double)rsvd_normal_at(p.seed, lin));
                         }
                     }
                     mbar_arrive(full_bar(s));
