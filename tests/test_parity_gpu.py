@@ -94,6 +94,29 @@ def test_svd_vs_reference_same_omega(api, oracle, m, n, k, p, vnum, q, s, spec):
         assert subspace_sin(U, Ur) < 1e-6 and subspace_sin(V, Vr) < 1e-6
 
 
+@pytest.mark.parametrize("m,n,k,p,q", [(10, 8, 3, 2, 2), (64, 64, 20, 44, 1), (33, 500, 16, 17, 2), (500, 33, 30, 3, 3), (257, 129, 1, 0, 2)])
+def test_svd_edge_shapes(api, oracle, m, n, k, p, q):
+    """tiny / ragged / extreme shapes: k+p == min(m,n), p == 0, k == 1, odd leading dimensions (no TMA alignment),
+    matrices smaller than one GEMM tile."""
+    rng = np.random.default_rng(m * n)
+    A = rng.standard_normal((m, n)) * np.logspace(0, -3, n)[None, :]
+    U, S, V = api.svd_rand(A, k, p, 1, q, 1, seed=4)
+    Ur, Sr, Vr = oracle.svd_rand(A, k, p, 1, q, 1, seed=4)
+    assert U.shape == (m, k) and S.shape == (k, k) and V.shape == (n, k)
+    assert rel_sigma_err(S, Sr) < 1e-9
+    assert abs(recon_err(A, U, S, V) - recon_err(A, Ur, Sr, Vr)) <= 0.01 * recon_err(A, Ur, Sr, Vr) + 1e-12
+
+
+def test_id_edge_shapes(api, oracle):
+    rng = np.random.default_rng(5)
+    for (m, n, k, p) in [(12, 9, 3, 2), (40, 300, 7, 3), (300, 40, 20, 20)]:
+        A = rng.standard_normal((m, n)) * np.logspace(0, -2, n)[None, :]
+        Ic, Ir, T, S = api.id_two_sided_rand(A, k, p, 1, 1, seed=6)
+        Icr, Irr, Tr, Sr = oracle.id_two_sided_rand(A, k, p, 1, 1, seed=6)
+        assert np.array_equal(Ic, Icr) and np.array_equal(Ir, Irr)
+        assert np.abs(T - Tr).max() < 1e-9 and np.abs(S - Sr).max() < 1e-9
+
+
 def test_svd_device_philox_different_seed_agrees_on_gap_spectrum(api, oracle):
     """'device Philox' mode of the north star: a different Omega must still give sigma to 1e-8 on a gap matrix."""
     A, sig = O.make_matrix(2000, 1500, "gap", seed=0, k=100, tail=1e-8)
