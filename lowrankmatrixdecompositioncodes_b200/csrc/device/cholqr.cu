@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(PB) potf2_inv_kernel(double *G, i64 ldg, i64 j
 
 int potrf_upper(double *G, i64 ldg, i64 n) {
     ensure_init();
+    if (g_status) return -1;
     int *flag = ctx().d_flag;
     RSVD_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx().stream));
     DBuf W((size_t)PB * PB), T((size_t)PB * (n > PB ? n - PB : 1));
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(PB) trtri_diag_kernel(const double *__restrict
 }
 
 void trtri_upper(const double *R, i64 ldr, i64 n, double *X, i64 ldx) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     ensure_init();
     if (n <= 0) return;
     // X = 0, then diagonal blocks
@@ -248,6 +250,7 @@ static int tsqr_r(const double *Y, i64 ldy, i64 m, i64 l, double *R /* l x l */,
 }
 
 void orthonormalize(double *Y, i64 ldy, i64 m, i64 l, double *R, i64 ldr, bool sharded, bool loose) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     ensure_init();
     if (m <= 0 || l <= 0) return;
     Ctx &c = ctx();

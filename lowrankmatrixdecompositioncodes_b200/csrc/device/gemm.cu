@@ -195,6 +195,7 @@ static void gemm_generic(const Gemm &g) {
 }
 
 void gemm(const Gemm &g) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     ensure_init();
     if (g.m <= 0 || g.n <= 0) return;
     if (!ctx().force_generic_gemm && gemm_tma_try(g)) { g_last_gemm_path = 1; return; }

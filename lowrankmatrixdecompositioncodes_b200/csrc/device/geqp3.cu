@@ -235,6 +235,7 @@ __global__ void int_to_double_kernel(const int *p, double *d, i64 n) {
 }
 
 void householder_qr(double *A, i64 lda, i64 m, i64 n, int pivoting, double *jpvt_out) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     ensure_init();
     Ctx &c = ctx();
     const i64 minmn = min(m, n);

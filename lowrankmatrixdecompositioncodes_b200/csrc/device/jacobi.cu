@@ -194,6 +194,7 @@ __global__ void finalize_kernel(const double *G, i64 ldg, const double *V, i64 l
 // core: G (n x n, destroyed) -> converged G = U*Sigma, V accumulated.  Returns sweeps used.
 int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
     Ctx &c = ctx();
+    if (g_status) return -1;   // an earlier error is pending: launch nothing
     set_identity(V, ldv, n);
     const int N = (n + 1) & ~1;
     if (n > JT * JR) { set_error("rsvd_b200: Jacobi kernel supports n <= %d (got %d)", JT * JR, n); return -1; }

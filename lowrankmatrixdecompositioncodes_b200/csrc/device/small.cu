@@ -21,6 +21,7 @@ __global__ void transpose_kernel(const double *__restrict__ A, i64 lda, double *
     }
 }
 void transpose(const double *A, i64 lda, double *B, i64 ldb, i64 m, i64 n) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     if (m <= 0 || n <= 0) return;
     // grid.y is limited to 65535 blocks: loop over column slabs if needed
     const i64 slab = 65535ll * 32;
@@ -46,6 +47,7 @@ static inline int grid_for(i64 total, int per = 256) {
     return (int)max((i64)1, min(b, cap));
 }
 void copy_matrix(const double *A, i64 lda, double *B, i64 ldb, i64 m, i64 n) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     if (m <= 0 || n <= 0) return;
     if (lda == m && ldb == m) {
         RSVD_CUDA(cudaMemcpyAsync(B, A, (size_t)m * n * 8, cudaMemcpyDeviceToDevice, ctx().stream));
@@ -64,6 +66,7 @@ __global__ void identity_kernel(double *A, i64 lda, i64 n) {
     }
 }
 void set_identity(double *A, i64 lda, i64 n) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     if (n <= 0) return;
     identity_kernel<<<grid_for(n * n), 256, 0, ctx().stream>>>(A, lda, n);
     count_launch();
@@ -76,6 +79,7 @@ __global__ void keep_upper_kernel(double *A, i64 lda, i64 n) {
     }
 }
 void keep_upper(double *A, i64 lda, i64 n) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     if (n <= 0) return;
     keep_upper_kernel<<<grid_for(n * n), 256, 0, ctx().stream>>>(A, lda, n);
     count_launch();
@@ -91,6 +95,7 @@ __global__ void gather_cols_kernel(const double *__restrict__ A, i64 lda, i64 m,
     }
 }
 void gather_cols(const double *A, i64 lda, i64 m, const double *idx, i64 k, double *B, i64 ldb) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     if (m <= 0 || k <= 0) return;
     gather_cols_kernel<<<grid_for(m * k), 256, 0, ctx().stream>>>(A, lda, m, idx, k, B, ldb);
     count_launch();
@@ -104,6 +109,7 @@ __global__ void gather_rows_kernel(const double *__restrict__ A, i64 lda, i64 n,
     }
 }
 void gather_rows(const double *A, i64 lda, i64 n, const double *idx, i64 k, double *B, i64 ldb) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     if (n <= 0 || k <= 0) return;
     gather_rows_kernel<<<grid_for(k * n), 256, 0, ctx().stream>>>(A, lda, n, idx, k, B, ldb);
     count_launch();
@@ -119,6 +125,7 @@ __global__ void scale_cols_kernel(double *A, i64 lda, i64 m, i64 n, const double
     }
 }
 void scale_cols(double *A, i64 lda, i64 m, i64 n, const double *s, int invert) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     if (m <= 0 || n <= 0) return;
     scale_cols_kernel<<<grid_for(m * n), 256, 0, ctx().stream>>>(A, lda, m, n, s, invert);
     count_launch();
@@ -163,6 +170,7 @@ __global__ void sum_final_kernel(const double *__restrict__ part, int n, double 
     }
 }
 void sumsq_async(const double *A, i64 lda, i64 m, i64 n, double *d_out) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     if (m <= 0 || n <= 0) { set_zero(d_out, 1); return; }
     int blocks = (int)min((i64)ctx().sms * 8, (m * n + 1023) / 1024);
     if (blocks < 1) blocks = 1;
@@ -173,6 +181,7 @@ void sumsq_async(const double *A, i64 lda, i64 m, i64 n, double *d_out) {
 }
 double frob_norm(const double *A, i64 lda, i64 m, i64 n) {
     ensure_init();
+    if (g_status) return -1.0;
     DBuf out(1);
     sumsq_async(A, lda, m, n, out.p);
     double h = 0.0;
@@ -238,6 +247,7 @@ __global__ void diag_inverse_kernel(const double *__restrict__ R, i64 ldr, i64 k
 }
 
 void trsm_left_upper(const double *R, i64 ldr, i64 k, double *B, i64 ldb, i64 ncols) {
+    if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     if (k <= 0 || ncols <= 0) return;
     const int nblk = (int)((k + TB - 1) / TB);
     DBuf dinv((size_t)nblk * TB * TB);
@@ -269,6 +279,7 @@ __global__ void __launch_bounds__(1024) lu_factor_kernel(double *A, i64 lda, int
 
 int lu_solve(double *A, i64 lda, i64 n, double *B, i64 ldb, i64 nrhs) {
     ensure_init();
+    if (g_status) return -1;
     if (n <= 0 || nrhs <= 0) return 0;
     int *flag = ctx().d_flag + 8;
     RSVD_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx().stream));

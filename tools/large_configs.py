@@ -13,16 +13,30 @@ sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")
 import lowrankmatrixdecompositioncodes_b200 as pkg  # noqa: E402
 from lowrankmatrixdecompositioncodes_b200 import device as D, native  # noqa: E402
 
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
 lib = native.dev()
-assert lib.rsvd_b200_init(0) == 0
+assert lib.rsvd_b200_init(local) == 0
 what = sys.argv[1] if len(sys.argv) > 1 else "c3"
+if world > 1:   # row-partitioned run under torchrun: one rank per GPU, NCCL for the n x l / l x l sums
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ident = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = C.create_string_buffer(128)
+        native.check(lib.rsvd_b200_comm_unique_id(buf))
+        ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    ident = ident.cuda()
+    dist.broadcast(ident, 0)
+    native.check(lib.rsvd_b200_comm_init(rank, world, bytes(ident.cpu().numpy().tobytes())))
 
 
 def gen(m, n, r=1280, lo=-3.0, noise=1e-8, seed=0):
     """A = X diag(sigma) W^T + noise, sigma = logspace(1, lo, r), built in HBM in column slabs (torch only generates data)."""
-    g = torch.Generator(device="cuda").manual_seed(seed)
-    X = torch.randn((m, r), dtype=torch.float64, device="cuda", generator=g) / m ** 0.5
-    W = torch.randn((n, r), dtype=torch.float64, device="cuda", generator=g) / n ** 0.5
+    g = torch.Generator(device="cuda").manual_seed(seed + 1000 * rank)      # this rank's rows
+    gw = torch.Generator(device="cuda").manual_seed(seed + 7)              # the same W on every rank
+    X = torch.randn((m, r), dtype=torch.float64, device="cuda", generator=g) / (m * world) ** 0.5
+    W = torch.randn((n, r), dtype=torch.float64, device="cuda", generator=gw) / n ** 0.5
     sig = torch.logspace(1, lo, r, dtype=torch.float64, device="cuda")
     A = torch.empty((n, m), dtype=torch.float64, device="cuda")
     step = 2048
@@ -66,29 +80,38 @@ if what == "c3":
     print("   ||Q^T Q - I||_max = %.2e" % (Qf @ Qf.t() - torch.eye(f, dtype=torch.float64, device="cuda")).abs().max().item())
 
 elif what == "c4":
-    m = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
+    mg = int(sys.argv[2]) if len(sys.argv) > 2 else 200000      # GLOBAL rows
     n, k, p, q, s = 50000, 1000, 20, 2, 1
+    r0, m = native.row_partition(mg, world, rank)
+    lib.rsvd_b200_set_option(b"row0", r0)
+    lib.rsvd_b200_set_option(b"m_global", mg)
     A, sig = gen(m, n, r=1536, lo=-2.0)
-    print("C4: id_two_sided_rand + cur_rand on %d x %d (%.1f GB), k=%d p=%d q=%d" % (m, n, 8e-9 * m * n, k, p, q), flush=True)
-    Icol = torch.empty(n, dtype=torch.float64, device="cuda"); Irow = torch.empty(m, dtype=torch.float64, device="cuda")
-    T = torch.empty((n - k, k), dtype=torch.float64, device="cuda"); Sm = torch.empty((m - k, k), dtype=torch.float64, device="cuda")
-    lib.rsvd_b200_set_option(b"verbose", 1)
+    if rank == 0:
+        print("C4: id_two_sided_rand + cur_rand on %d x %d (%.1f GB) over %d GPU(s), k=%d p=%d q=%d" % (mg, n, 8e-9 * mg * n, world, k, p, q), flush=True)
+    Icol = torch.empty(n, dtype=torch.float64, device="cuda"); Irow = torch.empty(mg, dtype=torch.float64, device="cuda")
+    T = torch.empty((n - k, k), dtype=torch.float64, device="cuda"); Sm = torch.empty((mg - k, k), dtype=torch.float64, device="cuda")
+    lib.rsvd_b200_set_option(b"verbose", 1 if rank == 0 else 0)
     sync()
     t0 = time.time()
     native.check(lib.rsvd_b200_id_two_sided_rand_dev(A.data_ptr(), m, n, m, k, p, q, s, 777, Icol.data_ptr(), Irow.data_ptr(), T.data_ptr(), k, Sm.data_ptr(), k))
     sync()
     dt = time.time() - t0
-    flops = (1 + 2 * q) * 2.0 * m * n * (k + p)
-    print("   two-sided ID: %.3f s  (%.1f TFLOP/s over the %d sketch/power passes alone)" % (dt, flops / dt / 1e12, 1 + 2 * q), flush=True)
+    flops = (1 + 2 * q) * 2.0 * mg * n * (k + p)
+    if rank == 0:
+        print("   two-sided ID: %.3f s  (%.1f TFLOP/s aggregate over the %d sketch/power passes alone)" % (dt, flops / dt / 1e12, 1 + 2 * q), flush=True)
     ic, ir = Icol.long(), Irow.long()
-    assert torch.equal(torch.sort(ic).values, torch.arange(n, device="cuda")) and torch.equal(torch.sort(ir).values, torch.arange(m, device="cuda"))
+    assert torch.equal(torch.sort(ic).values, torch.arange(n, device="cuda")) and torch.equal(torch.sort(ir).values, torch.arange(mg, device="cuda"))
+    if world > 1:   # replicated outputs must be identical on every rank
+        ref_ic = ic.clone(); dist.broadcast(ref_ic, 0)
+        assert torch.equal(ref_ic, ic), "Icol differs between ranks"
     # column-ID error on a row sample:  A(rows, Icol) ~ A(rows, Icol[:k]) [I T]
     rows = torch.randperm(m, device="cuda")[:4096]
     As = A.t()[rows]                                   # 4096 x n
     Ck = As[:, ic[:k]]
     err = (As[:, ic[k:]] - Ck @ T.t()).norm() / As.norm()
     opt = torch.sqrt((sig[k:] ** 2).sum()) / torch.sqrt((sig ** 2).sum())
-    print("   column ID rel. error on 4096 sampled rows: %.4e  (optimal rank-%d: %.4e)" % (err.item(), k, opt.item()), flush=True)
+    if rank == 0:
+        print("   column ID rel. error on 4096 sampled local rows: %.4e  (optimal rank-%d: %.4e)" % (err.item(), k, opt.item()), flush=True)
     del T, Sm
     Cm = D.new_cm(m, k); Um = D.new_cm(k, k); Rm = D.new_cm(k, n)
     sync()
@@ -96,10 +119,11 @@ elif what == "c4":
     native.check(lib.rsvd_b200_cur_rand_dev(A.data_ptr(), m, n, m, k, p, q, s, 777, Cm.data_ptr(), m, Um.data_ptr(), k, Rm.data_ptr(), k))
     sync()
     dt = time.time() - t0
-    print("   CUR (includes its own two-sided ID): %.3f s" % dt, flush=True)
     Cs = Cm.t()[rows]                                  # 4096 x k
     err = (As - Cs @ Um.t() @ Rm.t()).norm() / As.norm()
-    print("   CUR rel. error on the row sample: %.4e" % err.item(), flush=True)
+    if rank == 0:
+        print("   CUR (includes its own two-sided ID): %.3f s" % dt, flush=True)
+        print("   CUR rel. error on the row sample: %.4e" % err.item(), flush=True)
 
 elif what == "abi64":
     # int64 ABI end to end with m*n > 2^31 elements (the reason multi_core_mkl_code_64bit exists)
@@ -121,4 +145,8 @@ elif what == "abi64":
     rel = np.max(np.abs(np.diag(S) - sig[:k].cpu().numpy()) / sig[:k].cpu().numpy())
     api.lib.use_low_rank_svd_for_approximation(M, Um, Sm, Vm)
     print("   API call %.3f s; max rel deviation of sigma from the construction: %.2e; percent error %.4f" % (dt, rel, api.lib.rsvd_b200_api_last_percent_error()), flush=True)
-print("status:", lib.rsvd_b200_status(), lib.rsvd_b200_last_error())
+if rank == 0:
+    print("status:", lib.rsvd_b200_status(), lib.rsvd_b200_last_error())
+if world > 1:
+    lib.rsvd_b200_comm_destroy()
+    dist.destroy_process_group()
