@@ -112,7 +112,8 @@ elif what == "c4":
     opt = torch.sqrt((sig[k:] ** 2).sum()) / torch.sqrt((sig ** 2).sum())
     if rank == 0:
         print("   column ID rel. error on 4096 sampled local rows: %.4e  (optimal rank-%d: %.4e)" % (err.item(), k, opt.item()), flush=True)
-    del T, Sm
+    del T, Sm, Ck
+    torch.cuda.empty_cache()       # hand torch's cached blocks back: at 160 GB every GB counts
     Cm = D.new_cm(m, k); Um = D.new_cm(k, k); Rm = D.new_cm(k, n)
     sync()
     t0 = time.time()
