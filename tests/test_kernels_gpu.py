@@ -56,7 +56,11 @@ def test_generic_gemm(lib, ta, tb, m, n, k):
                                                  ("N", 1000, 130, 530, 1.5, 0.5), ("T", 778, 120, 2050, -1.0, 1.0),
                                                  ("T", 520, 520, 50000, 1.0, 0.0), ("N", 5000, 200, 200, -1.0, 1.0),
                                                  ("N", 4112, 520, 3000, 1.0, 0.0), ("N", 2050, 8, 700, 1.0, 0.0),
-                                                 ("T", 300, 1050, 4000, 1.0, 0.0)])
+                                                 ("T", 300, 1050, 4000, 1.0, 0.0),
+                                                 # every instantiated tile width: NB = 4, 8, 8, 14, 14 (two tiles), 15, 16
+                                                 ("N", 4000, 24, 600, 1.0, 0.0), ("T", 3000, 40, 600, 1.0, 0.0), ("N", 2000, 64, 500, 2.0, 1.0),
+                                                 ("N", 1200, 112, 500, 1.0, 0.0), ("T", 600, 216, 700, 1.0, 0.0), ("T", 1000, 120, 640, 1.0, 0.0),
+                                                 ("N", 1000, 128, 512, 1.0, 0.0)])
 def test_tma_gemm(lib, ta, m, n, k, alpha, beta):
     err, path = run_gemm(lib, ta, "N", m, n, k, alpha, beta, pad=0, force_generic=False)
     assert err < 2e-13
