@@ -104,14 +104,17 @@ __device__ __forceinline__ bool grid_barrier(int *bar, int gen, int *err) {
     return ok_s != 0;
 }
 
-// ctl[0] = barrier counter, ctl[1] = error flag, ctl[2] = sweeps done, ctl[8 + s] = CTAs that rotated in sweep s
+// ctl[0] = barrier counter, ctl[1] = error flag, ctl[2] = sweeps done, ctl[8 + s] = CTAs that rotated in sweep s,
+// (unsigned long long *)(ctl + 4)[0] = bit pattern of the largest |cosine| met in the current sweep (positive doubles order like integers)
 __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ldg, double *V, i64 ldv, int n, int N, double tol,
                                                                int max_sweeps, int *ctl) {
     __shared__ double sh[3 * (JT / 32)];
     const int i = blockIdx.x;
     int gen = 0;
+    unsigned long long *maxcos = reinterpret_cast<unsigned long long *>(ctl + 4);
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
         int rotated = 0;
+        double cmax = 0.0;
         for (int r = 0; r < N - 1; ++r) {
             int p, q;
             if (i == 0) { p = N - 1; q = r; }
@@ -137,6 +140,7 @@ __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ld
                     const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                     const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
                     rotated = 1;
+                    cmax = fmax(cmax, fabs(c) / sqrt(a * b));
 #pragma unroll
                     for (int k = 0; k < JR; ++k) {
                         int row = threadIdx.x + k * JT;
@@ -157,12 +161,18 @@ __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ld
                     }
                 }
             }
-            if (r == N - 2 && rotated && threadIdx.x == 0) atomicAdd(ctl + 8 + sweep, 1);
+            if (r == N - 2 && rotated && threadIdx.x == 0) {
+                atomicAdd(ctl + 8 + sweep, 1);
+                atomicMax(maxcos + (sweep & 1), (unsigned long long)__double_as_longlong(cmax));
+            }
             if (!grid_barrier(ctl, gen++, ctl + 1)) return;
         }
         const int nrot = *((volatile int *)(ctl + 8 + sweep));
-        if (blockIdx.x == 0 && threadIdx.x == 0) ctl[2] = sweep + 1;
-        if (nrot == 0) break;
+        const double swept = __longlong_as_double((long long)*((volatile unsigned long long *)(maxcos + (sweep & 1))));
+        if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[2] = sweep + 1; maxcos[(sweep + 1) & 1] = 0ull; }
+        // Converged when nothing was rotated, or when every cosine met in this sweep was already <= 1e-8: Jacobi converges
+        // quadratically, so the rotations just applied leave cosines of order 1e-16 and the confirming sweep is skipped.
+        if (nrot == 0 || swept <= 1.0e-8) break;
     }
 }
 
