@@ -107,15 +107,17 @@ __device__ __forceinline__ bool grid_barrier(int *bar, int gen, int *err) {
 // ctl[0] = barrier counter, ctl[1] = error flag, ctl[2] = sweeps done, ctl[8 + s] = CTAs that rotated in sweep s,
 // (unsigned long long *)(ctl + 4)[0] = bit pattern of the largest |cosine| met in the current sweep (positive doubles order like integers)
 __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ldg, double *V, i64 ldv, int n, int N, double tol,
-                                                               int max_sweeps, int *ctl) {
+                                                               int max_sweeps, int *ctl, double2 *rotlog) {
     __shared__ double sh[3 * (JT / 32)];
     const int i = blockIdx.x;
     int gen = 0;
     unsigned long long *maxcos = reinterpret_cast<unsigned long long *>(ctl + 4);
+    int gs = 0;      // global step index
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
         int rotated = 0;
         double cmax = 0.0;
-        for (int r = 0; r < N - 1; ++r) {
+        for (int r = 0; r < N - 1; ++r, ++gs) {
+            double2 applied = make_double2(1.0, 0.0);
             int p, q;
             if (i == 0) { p = N - 1; q = r; }
             else { p = (r + i) % (N - 1); q = (r - i + (N - 1)) % (N - 1); }
@@ -149,18 +151,23 @@ __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ld
                             gq[row] = sn * xp[k] + cs * xq[k];
                         }
                     }
-                    double *vp = V + (i64)p * ldv, *vq = V + (i64)q * ldv;
+                    applied = make_double2(cs, sn);
+                    if (!rotlog) {   // no log: rotate the columns of V in place
+                        double *vp = V + (i64)p * ldv, *vq = V + (i64)q * ldv;
 #pragma unroll
-                    for (int k = 0; k < JR; ++k) {
-                        int row = threadIdx.x + k * JT;
-                        if (row < n) {
-                            double y = __ldcg(vp + row), z = __ldcg(vq + row);
-                            vp[row] = cs * y - sn * z;
-                            vq[row] = sn * y + cs * z;
+                        for (int k = 0; k < JR; ++k) {
+                            int row = threadIdx.x + k * JT;
+                            if (row < n) {
+                                double y = __ldcg(vp + row), z = __ldcg(vq + row);
+                                vp[row] = cs * y - sn * z;
+                                vq[row] = sn * y + cs * z;
+                            }
                         }
                     }
                 }
             }
+            // the V update is off the critical path: the rotation is logged and replayed on V afterwards (jacobi_replay_kernel)
+            if (rotlog && threadIdx.x == 0) rotlog[(i64)gs * (N / 2) + i] = applied;
             if (r == N - 2 && rotated && threadIdx.x == 0) {
                 atomicAdd(ctl + 8 + sweep, 1);
                 atomicMax(maxcos + (sweep & 1), (unsigned long long)__double_as_longlong(cmax));
@@ -173,6 +180,43 @@ __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ld
         // Converged when nothing was rotated, or when every cosine met in this sweep was already <= 1e-8: Jacobi converges
         // quadratically, so the rotations just applied leave cosines of order 1e-16 and the confirming sweep is skipped.
         if (nrot == 0 || swept <= 1.0e-8) break;
+    }
+}
+
+// Replays the logged rotations on V = I.  One CTA owns RB rows of V (all n columns, in shared memory): rows are independent,
+// so the whole accumulated product of rotations costs a fraction of a millisecond instead of one dependent L2 round trip
+// per Jacobi step (measured: 1.6 of the 4.6 us of a step).
+constexpr int RB = 16;
+__global__ void __launch_bounds__(1024) jacobi_replay_kernel(double *V, i64 ldv, int n, int N, int total_steps, const double2 *__restrict__ rotlog) {
+    extern __shared__ double T[];          // [n][RB]
+    const int r0 = blockIdx.x * RB;
+    for (int e = threadIdx.x; e < n * RB; e += blockDim.x) {
+        const int col = e / RB, rr = e % RB;
+        T[e] = (col == r0 + rr) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int half = N / 2;
+    for (int gs = 0; gs < total_steps; ++gs) {
+        const int r = gs % (N - 1);
+        const double2 *lg = rotlog + (i64)gs * half;
+        for (int item = threadIdx.x; item < half * RB; item += blockDim.x) {
+            const int i = item / RB, rr = item % RB;
+            const double2 cssn = lg[i];
+            if (cssn.y != 0.0) {
+                int p, q;
+                if (i == 0) { p = N - 1; q = r; }
+                else { p = (r + i) % (N - 1); q = (r - i + (N - 1)) % (N - 1); }
+                if (p > q) { int t = p; p = q; q = t; }
+                const double x = T[p * RB + rr], y = T[q * RB + rr];
+                T[p * RB + rr] = cssn.x * x - cssn.y * y;
+                T[q * RB + rr] = cssn.y * x + cssn.x * y;
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < n * RB; e += blockDim.x) {
+        const int col = e / RB, rr = e % RB;
+        if (r0 + rr < n) V[(i64)col * ldv + r0 + rr] = T[e];
     }
 }
 
@@ -223,20 +267,37 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
         int *ctl = (int *)dalloc_bytes(64 * sizeof(int));
         RSVD_CUDA(cudaMemsetAsync(ctl, 0, 64 * sizeof(int), c.stream));
         int ms = max_sweeps;
-        void *args[] = {&G, &ldg, &V, &ldv, (void *)&n, (void *)&N, (void *)&tol, &ms, &ctl};
+        // rotation log for the deferred V update (identity entries where nothing was rotated); falls back to in-place V
+        // updates when the log would not fit the replay kernel's shared memory or 1 GiB
+        const int log_sweeps = 32;
+        const size_t log_entries = (size_t)log_sweeps * (N - 1) * (N / 2);
+        const size_t replay_smem = (size_t)n * RB * sizeof(double);
+        double2 *rotlog = nullptr;
+        if (replay_smem <= 200 * 1024 && log_entries * sizeof(double2) <= ((size_t)1 << 30) && !getenv("RSVD_B200_JACOBI_INPLACE_V")) {
+            rotlog = (double2 *)dalloc_bytes(log_entries * sizeof(double2));
+            ms = log_sweeps;
+        }
+        void *args[] = {&G, &ldg, &V, &ldv, (void *)&n, (void *)&N, (void *)&tol, &ms, &ctl, &rotlog};
         cudaError_t e = cudaLaunchCooperativeKernel((void *)jacobi_persistent_kernel, dim3(N / 2), dim3(JT), args, 0, c.stream);
         if (e == cudaSuccess) {
             count_launch();
             RSVD_CUDA(cudaMemcpyAsync(c.h_flag + 16, ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
             RSVD_CUDA(cudaStreamSynchronize(c.stream));
             dfree(ctl);
-            if (c.h_flag[17]) { set_error("rsvd_b200: Jacobi device-wide barrier timed out"); return -1; }
+            if (c.h_flag[17]) { set_error("rsvd_b200: Jacobi device-wide barrier timed out"); if (rotlog) dfree(rotlog); return -1; }
             sweeps = c.h_flag[18];
+            if (rotlog) {
+                RSVD_CUDA(cudaFuncSetAttribute(jacobi_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)replay_smem));
+                jacobi_replay_kernel<<<(n + RB - 1) / RB, 1024, replay_smem, c.stream>>>(V, ldv, n, N, sweeps * (N - 1), rotlog);
+                count_launch();
+                dfree(rotlog);
+            }
             if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d (persistent)\n", n, sweeps);
             return sweeps;
         }
         (void)cudaGetLastError();
         dfree(ctl);
+        if (rotlog) dfree(rotlog);
     }
 
     // fallback: one kernel per step, a whole sweep replayed from a CUDA graph
