@@ -183,41 +183,73 @@ __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ld
     }
 }
 
-// Replays the logged rotations on V = I.  One CTA owns RB rows of V (all n columns, in shared memory): rows are independent,
-// so the whole accumulated product of rotations costs a fraction of a millisecond instead of one dependent L2 round trip
-// per Jacobi step (measured: 1.6 of the 4.6 us of a step).
-constexpr int RB = 16;
-__global__ void __launch_bounds__(1024) jacobi_replay_kernel(double *V, i64 ldv, int n, int N, int total_steps, const double2 *__restrict__ rotlog) {
-    extern __shared__ double T[];          // [n][RB]
-    const int r0 = blockIdx.x * RB;
-    for (int e = threadIdx.x; e < n * RB; e += blockDim.x) {
-        const int col = e / RB, rr = e % RB;
+// Replays the logged rotations on V = I.  Rows of V are independent, so one CTA owns RR rows (all N columns, in shared
+// memory) and one thread owns pair slot i: a step is one rotation of RR-row column pieces per thread and one __syncthreads,
+// with the log entries of the next RPB steps prefetched while the current RPB are applied.  The whole accumulated product
+// costs about a millisecond instead of one dependent L2 round trip per Jacobi step (measured: 1.6 of the 4.6 us of a step).
+constexpr int RPB = 8;
+template <int RR>
+__global__ void __launch_bounds__(RR == 4 ? 608 : 1024) jacobi_replay_kernel(double *V, i64 ldv, int n, int N, int total_steps,
+                                                             const double2 *__restrict__ rotlog) {
+    extern __shared__ __align__(16) double T[];          // [N][RR]
+    const int r0 = blockIdx.x * RR;
+    for (int e = threadIdx.x; e < N * RR; e += blockDim.x) {
+        const int col = e / RR, rr = e % RR;
         T[e] = (col == r0 + rr) ? 1.0 : 0.0;
     }
     __syncthreads();
     const int half = N / 2;
-    for (int gs = 0; gs < total_steps; ++gs) {
-        const int r = gs % (N - 1);
-        const double2 *lg = rotlog + (i64)gs * half;
-        for (int item = threadIdx.x; item < half * RB; item += blockDim.x) {
-            const int i = item / RB, rr = item % RB;
-            const double2 cssn = lg[i];
-            if (cssn.y != 0.0) {
-                int p, q;
-                if (i == 0) { p = N - 1; q = r; }
-                else { p = (r + i) % (N - 1); q = (r - i + (N - 1)) % (N - 1); }
-                if (p > q) { int t = p; p = q; q = t; }
-                const double x = T[p * RB + rr], y = T[q * RB + rr];
-                T[p * RB + rr] = cssn.x * x - cssn.y * y;
-                T[q * RB + rr] = cssn.y * x + cssn.x * y;
+    const int i = threadIdx.x;
+    const bool active = i < half;
+    const double2 ident = make_double2(1.0, 0.0);
+    double2 cur[RPB], nxt[RPB];
+#pragma unroll
+    for (int b = 0; b < RPB; ++b) cur[b] = (active && b < total_steps) ? __ldg(rotlog + (i64)b * half + i) : ident;
+    int r = 0;
+    for (int base = 0; base < total_steps; base += RPB) {
+#pragma unroll
+        for (int b = 0; b < RPB; ++b) {
+            const int g = base + RPB + b;
+            nxt[b] = (active && g < total_steps) ? __ldg(rotlog + (i64)g * half + i) : ident;
+        }
+#pragma unroll
+        for (int b = 0; b < RPB; ++b) {
+            if (base + b < total_steps) {     // uniform
+                if (cur[b].y != 0.0) {        // identity entries (nothing rotated, padded column, inactive thread) are skipped
+                    int p, q;
+                    if (i == 0) { p = N - 1; q = r; }
+                    else {
+                        p = r + i; if (p >= N - 1) p -= N - 1;
+                        q = r - i; if (q < 0) q += N - 1;
+                    }
+                    if (p > q) { int t = p; p = q; q = t; }
+                    double2 *tp = reinterpret_cast<double2 *>(T + p * RR), *tq = reinterpret_cast<double2 *>(T + q * RR);
+                    const double cs = cur[b].x, sn = cur[b].y;
+#pragma unroll
+                    for (int h = 0; h < RR / 2; ++h) {
+                        const double2 x = tp[h], y = tq[h];
+                        tp[h] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
+                        tq[h] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
+                    }
+                }
+                if (++r == N - 1) r = 0;
+                __syncthreads();
             }
         }
-        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < RPB; ++b) cur[b] = nxt[b];
     }
-    for (int e = threadIdx.x; e < n * RB; e += blockDim.x) {
-        const int col = e / RB, rr = e % RB;
+    for (int e = threadIdx.x; e < n * RR; e += blockDim.x) {
+        const int col = e / RR, rr = e % RR;
         if (r0 + rr < n) V[(i64)col * ldv + r0 + rr] = T[e];
     }
+}
+
+template <int RR>
+static void launch_replay(double *V, i64 ldv, int n, int N, int steps, const double2 *rotlog, cudaStream_t st) {
+    const size_t smem = (size_t)N * RR * sizeof(double);
+    RSVD_CUDA(cudaFuncSetAttribute(jacobi_replay_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jacobi_replay_kernel<RR><<<(n + RR - 1) / RR, (N / 2 + 31) / 32 * 32, smem, st>>>(V, ldv, n, N, steps, rotlog);
 }
 
 // sigma[j] = ||G(:,j)||, one warp per column
@@ -269,14 +301,10 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
         int ms = max_sweeps;
         // rotation log for the deferred V update (identity entries where nothing was rotated); falls back to in-place V
         // updates when the log would not fit the replay kernel's shared memory or 1 GiB
-        const int log_sweeps = 32;
-        const size_t log_entries = (size_t)log_sweeps * (N - 1) * (N / 2);
-        const size_t replay_smem = (size_t)n * RB * sizeof(double);
+        const size_t log_entries = (size_t)max_sweeps * (N - 1) * (N / 2);
         double2 *rotlog = nullptr;
-        if (replay_smem <= 200 * 1024 && log_entries * sizeof(double2) <= ((size_t)1 << 30) && !getenv("RSVD_B200_JACOBI_INPLACE_V")) {
+        if (N / 2 <= 1024 && log_entries * sizeof(double2) <= ((size_t)1 << 30) && !getenv("RSVD_B200_JACOBI_INPLACE_V"))
             rotlog = (double2 *)dalloc_bytes(log_entries * sizeof(double2));
-            ms = log_sweeps;
-        }
         void *args[] = {&G, &ldg, &V, &ldv, (void *)&n, (void *)&N, (void *)&tol, &ms, &ctl, &rotlog};
         cudaError_t e = cudaLaunchCooperativeKernel((void *)jacobi_persistent_kernel, dim3(N / 2), dim3(JT), args, 0, c.stream);
         if (e == cudaSuccess) {
@@ -287,8 +315,8 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
             if (c.h_flag[17]) { set_error("rsvd_b200: Jacobi device-wide barrier timed out"); if (rotlog) dfree(rotlog); return -1; }
             sweeps = c.h_flag[18];
             if (rotlog) {
-                RSVD_CUDA(cudaFuncSetAttribute(jacobi_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)replay_smem));
-                jacobi_replay_kernel<<<(n + RB - 1) / RB, 1024, replay_smem, c.stream>>>(V, ldv, n, N, sweeps * (N - 1), rotlog);
+                if (n <= 1184) launch_replay<4>(V, ldv, n, N, sweeps * (N - 1), rotlog, c.stream);   // <= 2 CTAs per SM, one wave
+                else launch_replay<8>(V, ldv, n, N, sweeps * (N - 1), rotlog, c.stream);
                 count_launch();
                 dfree(rotlog);
             }
