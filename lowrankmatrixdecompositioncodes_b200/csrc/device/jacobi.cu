@@ -89,15 +89,17 @@ __device__ __forceinline__ bool grid_barrier(int *bar, int gen, int *err) {
     __syncthreads();
     __shared__ int ok_s;
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1);
+        // release arrive / acquire poll: bar.sync orders the CTA's stores before the release (cumulativity), and the acquire
+        // before the CTA's next loads.  Much cheaper than a pair of sequentially-consistent fences around a relaxed atomic.
+        asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(bar) : "memory");
         const int target = (gen + 1) * (int)gridDim.x;
-        int ok = 1;
+        int ok = 1, seen;
         long long spins = 0;
-        while (*((volatile int *)bar) < target) {
-            if (++spins > (1ll << 26) || *((volatile int *)err)) { ok = 0; *err = 1; break; }
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+            if (seen >= target) break;
+            if ((++spins & 1023) == 0 && (spins > (1ll << 26) || *((volatile int *)err))) { ok = 0; *err = 1; break; }
         }
-        __threadfence();
         ok_s = ok;
     }
     __syncthreads();
