@@ -118,6 +118,36 @@ int rsvd_b200_id_two_sided_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsv
 /* cur_rand_decomp_fixed_rank (RRA:2191-2258). C m x k, U k x k, R k x n. */
 int rsvd_b200_cur_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q, int s,
                            uint64_t seed, double *C, rsvd_i64 ldc, double *U, rsvd_i64 ldu, double *R, rsvd_i64 ldr);
+/* ---- deterministic baselines and legacy entry points ---- */
+/* randQB_pb (RRA:1425-1572): as randqb_dev in rank mode but re-orthogonalising against all previous blocks on EVERY step
+ * (RRA:1503-1528); p = power steps (loop j <= p), no tolerance.  Q m x kstep*nstep, B kstep*nstep x n. */
+int rsvd_b200_randqb_legacy_dev(double *Awork, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 kstep, rsvd_i64 nstep, int p, int s,
+                                uint64_t seed, double *Q, rsvd_i64 ldq, double *B, rsvd_i64 ldb);
+/* randQB_p (RRA:1343-1421): single-vector randQB, k columns one at a time with p power steps each (BLAS-2, HBM-bound). */
+int rsvd_b200_randqb_single_dev(double *Awork, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, uint64_t seed, double *Q,
+                                rsvd_i64 ldq, double *B, rsvd_i64 ldb);
+/* SVD factors from (Q, B) in ASCENDING singular-value order: tail of randomized_low_rank_svd4 (RRA:660-688, dsyev order). */
+int rsvd_b200_svd_from_qb_asc_dev(const double *Q, rsvd_i64 m, rsvd_i64 ldq, const double *B, rsvd_i64 l, rsvd_i64 n, rsvd_i64 ldb, double *U,
+                                  rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv);
+/* full thin SVD A = U diag(S) V^T, r = min(m,n) (dgesvd 'S','S' of low_rank_svd_decomp_fixed_rank_or_prec, RRA:7-69); r <= 1280 (Jacobi kernel limit). */
+int rsvd_b200_svd_full_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, double *U, rsvd_i64 ldu, double *S, double *V,
+                           rsvd_i64 ldv);
+/* estimate_rank_and_buildQ (MVF:1339-1400): sketch of width maxdim, sequential Gram-Schmidt with the reference's stop rule;
+ * Q is an m x maxdim buffer whose first *rank columns are the orthonormal basis. */
+int rsvd_b200_estimate_rank1_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 maxdim, double tol, uint64_t seed, double *Q,
+                                 rsvd_i64 ldq, rsvd_i64 *rank);
+/* estimate_rank_and_buildQ2 (MVF:1404-1467): sketch grown by kblock columns until ||QQ^T A - A||_F/||QQ^T A||_F <= tol or max_cols.
+ * Y, Q: m x max_cols buffers; *rank = columns used.  Successive blocks continue the Philox stream. */
+int rsvd_b200_estimate_rank2_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 kblock, double tol, uint64_t seed, double *Y,
+                                 rsvd_i64 ldy, double *Q, rsvd_i64 ldq, rsvd_i64 max_cols, rsvd_i64 *rank);
+/* power iterations (loop j < q, RRA:858-886) + SVD tail from an existing sketch Y = A*Omega (m x l): U m x l, S l, V n x l. */
+int rsvd_b200_svd_rand_from_sketch_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, double *Y, rsvd_i64 ldy, rsvd_i64 l, int q, int s,
+                                       double *U, rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv);
+/* the reference's own partial pivoted Householder QR (pivoted_QR_of_specified_rank, RRA:1012-1155, with zero_exact = 1;
+ * pivoted_QR_of_specified_rank_or_prec, RRA:1159-1334, with zero_exact = 0).  k > 0: at most k steps; k <= 0: tolerance mode.
+ * Awork (m x n) is destroyed.  *frank = steps taken; I n doubles (0-based); Q m x frank; R frank x n (any may be NULL). */
+int rsvd_b200_pqr_partial_dev(double *Awork, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n, rsvd_i64 k, double tol, int zero_exact, double *I,
+                              double *Q, rsvd_i64 ldq, double *R, rsvd_i64 ldr, rsvd_i64 *frank);
 /* streamed 100*||A - U diag(S) V^T||_F/||A||_F (get_percent_error_between_two_mats after form_svd_product_matrix,
  * MVF:391-405,1304-1318) without forming the dense m x n product at once. */
 double rsvd_b200_svd_percent_error_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, const double *U, rsvd_i64 ldu,

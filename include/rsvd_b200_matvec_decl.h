@@ -147,6 +147,11 @@ void form_cur_product_matrix(mat *C, mat *U, mat *R, mat *P);       /* P = C U R
 void upper_triangular_system_solve(mat *A, mat *B, mat *X, int solve_type);
 void square_matrix_system_solve(mat *A, mat *X, mat *B);
 
+/* legacy range-finder helpers (MVH:226, 241, 342, 345) */
+void project_vector(vec *v, vec *u, vec *p);
+void build_orthonormal_basis_from_mat(mat *A, mat *Q);
+void estimate_rank_and_buildQ(mat *M, double frac_of_max_rank, double TOL, mat **Q, RSVD_INT *good_rank);
+void estimate_rank_and_buildQ2(mat *M, RSVD_INT kblock, double TOL, mat **Y, mat **Q, RSVD_INT *good_rank);
 double get_seconds_frac(struct timeval start_timeval, struct timeval end_timeval);
 
 #ifdef __cplusplus

@@ -50,6 +50,26 @@ void use_id_decomp_for_approximation(mat *M, mat *T, vec *I, RSVD_INT k);
 void use_id_two_sided_decomp_for_approximation(mat *M, mat *T, mat *S, vec *Icol, vec *Irow, RSVD_INT k);
 void use_cur_decomp_for_approximation(mat *M, mat *C, mat *U, mat *R);
 
+/* ---- deterministic baselines (RRH:11, 44-51, 65, 75, 85, 98) ---- */
+void low_rank_svd_decomp_fixed_rank_or_prec(mat *M, RSVD_INT k, double TOL, RSVD_INT *frank, mat **U, mat **S, mat **V);
+void get_householder_matrix(vec *x, RSVD_INT ind1, RSVD_INT ind2, mat *H);
+void pivoted_QR_of_specified_rank(mat *M, RSVD_INT k, RSVD_INT *frank, mat **Qk, mat **Rk, vec **I);
+void pivoted_QR_of_specified_rank_or_prec(mat *M, RSVD_INT k, double TOL, RSVD_INT *frank, mat **Qk, mat **Rk, vec **I);
+void id_two_sided_decomp_fixed_rank_or_prec(mat *M, RSVD_INT k, double TOL, RSVD_INT *frank, vec **Icol, vec **Irow, mat **T, mat **S);
+void cur_decomp_fixed_rank_or_prec(mat *M, RSVD_INT k, double TOL, RSVD_INT *frank, mat **C, mat **U, mat **R);
+void use_pivoted_QR_decomp_for_approximation(mat *M, mat *Qk, mat *Rk, vec *I);
+
+/* ---- legacy entry points (RRH:14-37, 54-57) ---- */
+void randomized_low_rank_svd1(mat *M, RSVD_INT k, mat **U, mat **S, mat **V);
+void randomized_low_rank_svd2(mat *M, RSVD_INT k, mat **U, mat **S, mat **V);
+void randomized_low_rank_svd3(mat *M, RSVD_INT k, RSVD_INT q, RSVD_INT s, mat **U, mat **S, mat **V);
+void randomized_low_rank_svd4(mat *M, RSVD_INT kstep, RSVD_INT nstep, RSVD_INT p, mat **U, mat **S, mat **V);
+void randomized_low_rank_svd2_autorank1(mat *M, double frac_of_max_rank, double TOL, mat **U, mat **S, mat **V);
+void randomized_low_rank_svd2_autorank2(mat *M, RSVD_INT kblocksize, double TOL, mat **U, mat **S, mat **V);
+void randomized_low_rank_svd3_autorank2(mat *M, RSVD_INT kblocksize, double TOL, RSVD_INT q, RSVD_INT s, mat **U, mat **S, mat **V);
+void randQB_p(mat *M, RSVD_INT k, RSVD_INT p, mat **Q, mat **B);
+void randQB_pb(mat *M, RSVD_INT kstep, RSVD_INT nstep, RSVD_INT p, RSVD_INT s, mat **Q, mat **B);
+
 /* ---- out-of-band status (the reference API is void and unchecked) ---- */
 int rsvd_b200_api_status(void);                 /* 0 = last call succeeded */
 const char *rsvd_b200_api_last_error(void);

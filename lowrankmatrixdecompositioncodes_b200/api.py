@@ -7,9 +7,10 @@ import ctypes as C
 import numpy as np
 
 from . import native
+from . import _legacy_calls
 
 
-class Api:
+class Api(_legacy_calls.LegacyCalls):
     def __init__(self, bits=32):
         native.dev()  # device layer first (RTLD_GLOBAL)
         self.bits = bits
@@ -68,6 +69,7 @@ class Api:
         L.use_id_decomp_for_approximation.argtypes = [PM, PM, PV, I]
         L.use_id_two_sided_decomp_for_approximation.argtypes = [PM, PM, PM, PV, PV, I]
         L.use_cur_decomp_for_approximation.argtypes = [PM, PM, PM, PM]
+        _legacy_calls.bind(L, I, PM, PV)
         L.rsvd_b200_api_status.restype = C.c_int
         L.rsvd_b200_api_last_error.restype = C.c_char_p
         L.rsvd_b200_api_last_percent_error.restype = C.c_double

@@ -9,7 +9,14 @@ int svd_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int vnum, int
 int svd_rand_host(const double *hA, double *dA, i64 m, i64 n, i64 k, i64 p, int vnum, int q, int s, uint64_t seed, double *U, i64 ldu,
                   double *S, double *V, i64 ldv);
 int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, int q, int s, uint64_t seed, double *Q,
-           i64 ldq, double *B, i64 ldb, i64 max_rank, i64 *frank_out);
+           i64 ldq, double *B, i64 ldb, i64 max_rank, i64 *frank_out, int legacy_reorth);
+int randqb_single(double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, uint64_t seed, double *Q, i64 ldq, double *B, i64 ldb);
+int svd_full(const double *A, i64 m, i64 n, i64 lda, double *U, i64 ldu, double *S, double *V, i64 ldv);
+int estimate_rank1(const double *A, i64 m, i64 n, i64 lda, i64 maxdim, double tol, uint64_t seed, double *Q, i64 ldq, i64 *rank_out);
+int estimate_rank2(const double *A, i64 m, i64 n, i64 lda, i64 kblock, double tol, uint64_t seed, double *Y, i64 ldy, double *Q, i64 ldq,
+                   i64 max_cols, i64 *rank_out);
+int svd_rand_from_sketch(const double *A, i64 m, i64 n, i64 lda, double *Y, i64 ldy, i64 l, int q, int s, double *U, i64 ldu,
+                         double *S, double *V, i64 ldv);
 int id_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, const double *omega,
             double *I, double *T, i64 ldt);
 int id_full(const double *M, i64 k, i64 n, i64 ldm, double *I, double *T, i64 ldt);
@@ -17,7 +24,8 @@ int id_qr(const double *M, i64 r, i64 n, i64 ldm, i64 k, double *I, double *T, i
 int id_rows(const double *A, i64 m, i64 n, i64 lda, const double *Icol, i64 k, double *Irow, double *S, i64 lds, i64 m_global);
 int cur_from_id(const double *A, i64 m, i64 n, i64 lda, const double *Icol, const double *Irow, const double *T, i64 ldt, i64 k,
                 double *Cm, i64 ldc, double *U, i64 ldu, double *R, i64 ldr);
-int svd_from_qb(const double *Q, i64 m, i64 ldq, const double *B, i64 l, i64 n, i64 ldb, double *U, i64 ldu, double *S, double *V, i64 ldv);
+int svd_from_qb(const double *Q, i64 m, i64 ldq, const double *B, i64 l, i64 n, i64 ldb, double *U, i64 ldu, double *S, double *V, i64 ldv,
+                int ascending);
 int id_two_sided_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, double *Icol,
                       double *Irow, double *T, i64 ldt, double *S, i64 lds, i64 m_global);
 int cur_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, double *Cm, i64 ldc,
@@ -149,7 +157,52 @@ int rsvd_b200_randqb_dev(double *Awork, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rs
                          int q, int s, uint64_t seed, double *Q, rsvd_i64 ldq, double *B, rsvd_i64 ldb, rsvd_i64 *frank) {
     READY();
     // capacity of Q/B in columns/rows: ldb rows of B were allocated by the caller
-    return finish(randqb(Awork, m, n, lda, kstep, nstep, tol, q, s, seed, Q, ldq, B, ldb, ldb, frank));
+    return finish(randqb(Awork, m, n, lda, kstep, nstep, tol, q, s, seed, Q, ldq, B, ldb, ldb, frank, 0));
+}
+
+int rsvd_b200_randqb_legacy_dev(double *Awork, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 kstep, rsvd_i64 nstep, int p, int s,
+                                uint64_t seed, double *Q, rsvd_i64 ldq, double *B, rsvd_i64 ldb) {
+    READY();
+    if (nstep <= 0) { set_error("rsvd_b200: randQB_pb needs nstep > 0"); return 1; }
+    i64 frank = 0;
+    return finish(randqb(Awork, m, n, lda, kstep, nstep, 0.0, p, s, seed, Q, ldq, B, ldb, ldb, &frank, 1));
+}
+
+int rsvd_b200_randqb_single_dev(double *Awork, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, uint64_t seed, double *Q,
+                                rsvd_i64 ldq, double *B, rsvd_i64 ldb) {
+    READY();
+    return finish(randqb_single(Awork, m, n, lda, k, p, seed, Q, ldq, B, ldb));
+}
+
+int rsvd_b200_svd_full_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, double *U, rsvd_i64 ldu, double *S, double *V,
+                           rsvd_i64 ldv) {
+    READY();
+    return finish(svd_full(A, m, n, lda, U, ldu, S, V, ldv));
+}
+
+int rsvd_b200_estimate_rank1_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 maxdim, double tol, uint64_t seed, double *Q,
+                                 rsvd_i64 ldq, rsvd_i64 *rank) {
+    READY();
+    return finish(estimate_rank1(A, m, n, lda, maxdim, tol, seed, Q, ldq, rank));
+}
+
+int rsvd_b200_estimate_rank2_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 kblock, double tol, uint64_t seed, double *Y,
+                                 rsvd_i64 ldy, double *Q, rsvd_i64 ldq, rsvd_i64 max_cols, rsvd_i64 *rank) {
+    READY();
+    return finish(estimate_rank2(A, m, n, lda, kblock, tol, seed, Y, ldy, Q, ldq, max_cols, rank));
+}
+
+int rsvd_b200_svd_rand_from_sketch_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, double *Y, rsvd_i64 ldy, rsvd_i64 l, int q, int s,
+                                       double *U, rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv) {
+    READY();
+    return finish(svd_rand_from_sketch(A, m, n, lda, Y, ldy, l, q, s, U, ldu, S, V, ldv));
+}
+
+int rsvd_b200_pqr_partial_dev(double *Awork, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n, rsvd_i64 k, double tol, int zero_exact, double *I,
+                              double *Q, rsvd_i64 ldq, double *R, rsvd_i64 ldr, rsvd_i64 *frank) {
+    READY();
+    *frank = pqr_partial(Awork, lda, m, n, k, tol, zero_exact, I, Q, ldq, R, ldr);
+    return finish(g_status);
 }
 
 int rsvd_b200_svd_from_q_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, double *Q, rsvd_i64 ldq, rsvd_i64 l,
@@ -189,7 +242,13 @@ int rsvd_b200_cur_from_id_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 
 int rsvd_b200_svd_from_qb_dev(const double *Q, rsvd_i64 m, rsvd_i64 ldq, const double *B, rsvd_i64 l, rsvd_i64 n, rsvd_i64 ldb, double *U,
                               rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv) {
     READY();
-    return finish(svd_from_qb(Q, m, ldq, B, l, n, ldb, U, ldu, S, V, ldv));
+    return finish(svd_from_qb(Q, m, ldq, B, l, n, ldb, U, ldu, S, V, ldv, 0));
+}
+
+int rsvd_b200_svd_from_qb_asc_dev(const double *Q, rsvd_i64 m, rsvd_i64 ldq, const double *B, rsvd_i64 l, rsvd_i64 n, rsvd_i64 ldb, double *U,
+                                  rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv) {
+    READY();
+    return finish(svd_from_qb(Q, m, ldq, B, l, n, ldb, U, ldu, S, V, ldv, 1));
 }
 
 int rsvd_b200_id_two_sided_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q,

@@ -106,6 +106,10 @@ void sumsq_async(const double *A, i64 lda, i64 m, i64 n, double *d_out);      //
 void fill_normal(double *A, i64 n_entries, uint64_t seed, i64 first);
 void trsm_left_upper(const double *R, i64 ldr, i64 k, double *B, i64 ldb, i64 ncols);  // B <- R^{-1} B
 int lu_solve(double *A, i64 lda, i64 n, double *B, i64 ldb, i64 nrhs);        // dgesv semantics, in place
+void gemv(char trans, i64 m, i64 n, double alpha, const double *A, i64 lda, const double *x, double beta, double *y);
+void rank1_update(double *A, i64 lda, i64 m, i64 n, const double *q, const double *b);   // A -= q b^T
+void scale_by_inv_norm(const double *y, i64 m, const double *sumsq, double *q);          // q = y / sqrt(*sumsq)
+i64 mgs_rank_estimate(double *Q, i64 ldq, i64 m, i64 maxdim, double tol);                // MGS + stop rule of MVF:1366-1388; syncs
 
 // ---- orthonormalisation (cholqr.cu) ------------------------------------------------------------
 // Q (m x l, ld) <- orthonormal basis of range(Y); in place. If R != nullptr also returns R (l x l upper).
@@ -121,6 +125,8 @@ void trtri_upper(const double *R, i64 ldr, i64 n, double *Rinv, i64 ldi); // Rin
 void geqp3(double *A, i64 lda, i64 m, i64 n, double *jpvt_out);
 // unpivoted Householder, R only (upper triangle of A on exit), used by the TSQR fallback
 void geqrf_r(double *A, i64 lda, i64 m, i64 n);
+// the reference's own partial pivoted QR (RRA:1012-1334); returns frank
+i64 pqr_partial(double *A, i64 lda, i64 m, i64 n, i64 k, double tol, int zero_exact, double *I, double *Q, i64 ldq, double *R, i64 ldr);
 
 // ---- small dense eigen/SVD (jacobi.cu) ---------------------------------------------------------
 // A (n x n, overwritten) = U diag(s) V^T, s descending. U (n x n), Vt (n x n).

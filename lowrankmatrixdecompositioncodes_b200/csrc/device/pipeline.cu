@@ -85,6 +85,14 @@ __global__ void gather_rows_owned_kernel(const double *A, i64 lda, i64 mloc, i64
     }
 }
 
+// in-place column reversal of A (m x n) and of the n-vector s
+__global__ void reverse_cols_kernel(double *A, i64 lda, i64 m, i64 n, double *s) {
+    const i64 j = blockIdx.x, jj = n - 1 - j;
+    if (j >= jj) return;
+    for (i64 r = threadIdx.x; r < m; r += blockDim.x) { double t = A[j * lda + r]; A[j * lda + r] = A[jj * lda + r]; A[jj * lda + r] = t; }
+    if (threadIdx.x == 0 && s) { double t = s[j]; s[j] = s[jj]; s[jj] = t; }
+}
+
 // device-side tolerance test of randQB_pb_new (RRA:1771-1777): done = (sqrt(sumsq) < tol)
 __global__ void tol_check_kernel(const double *sumsq, double tol, int *done, double *norm_out) {
     double nv = sqrt(sumsq[0]);
@@ -220,8 +228,10 @@ int svd_rand_host(const double *hA, double *dA, i64 m, i64 n, i64 k, i64 p, int 
 // ---------------------------------------------------------------------------------------------------------
 // randQB_pb_new (RRA:1576-1801)
 // ---------------------------------------------------------------------------------------------------------
+// legacy_reorth: re-orthogonalise Qp against Q(:, 0:c0) on EVERY step > 0 as randQB_pb does (RRA:1503-1528) instead of on
+// even steps only (randQB_pb_new, RRA:1703).
 int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, int q, int s, uint64_t seed,
-           double *Q, i64 ldq, double *B, i64 ldb, i64 max_rank, i64 *frank_out) {
+           double *Q, i64 ldq, double *B, i64 ldb, i64 max_rank, i64 *frank_out, int legacy_reorth) {
     ensure_init();
     Ctx &c = ctx();
     if (!c.inited) return 1;
@@ -243,7 +253,7 @@ int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, i
             mm('N', 'N', m, kstep, n, 1.0, A, lda, W.p, n, 0.0, Yp.p, m);           // Yp = A AtQp2 (RRA:1674 / 1681)
         }
         orthonormalize(Yp.p, m, m, kstep, nullptr, 0, true);                        // Qp (RRA:1690)
-        if (step > 0 && step % 2 == 0) {                                            // RRA:1703-1722
+        if (step > 0 && (legacy_reorth || step % 2 == 0)) {                         // RRA:1703-1722
             DBuf T((size_t)c0 * kstep);
             mm('T', 'N', c0, kstep, m, 1.0, Q, ldq, Yp.p, m, 0.0, T.p, c0);
             allreduce_sum(T.p, (size_t)c0 * kstep);
@@ -424,8 +434,9 @@ int cur_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s,
 
 // low_rank_svd_rand_decomp_fromQB (oneapi_code/rank_revealing_algorithms_one_api.c:244-304, restated in FP64):
 // B B^T = Uhat S^2 Uhat^T (descending), U = Q Uhat, V = B^T Uhat S^{-1}; all l = rows(B) triplets are returned.
+// ascending != 0: factors ordered by ascending singular value, the dsyev order randomized_low_rank_svd4 returns (RRA:664-688)
 int svd_from_qb(const double *Q, i64 m, i64 ldq, const double *B, i64 l, i64 n, i64 ldb, double *U, i64 ldu, double *S,
-                double *V, i64 ldv) {
+                double *V, i64 ldv, int ascending) {
     ensure_init();
     Ctx &c = ctx();
     if (!c.inited) return 1;
@@ -435,11 +446,134 @@ int svd_from_qb(const double *Q, i64 m, i64 ldq, const double *B, i64 l, i64 n, 
     jacobi_svd(BBt.p, l, l, Uhat.p, l, S, Vt.p, l);                                  // :268
     sqrt_clamp_kernel<<<(unsigned)((l + 127) / 128), 128, 0, c.stream>>>(S, (int)l); // :277-280
     count_launch();
+    if (ascending) {
+        reverse_cols_kernel<<<(unsigned)((l + 1) / 2 > 0 ? (l + 1) / 2 : 1), 128, 0, c.stream>>>(Uhat.p, l, l, l, S);
+        count_launch();
+    }
     mm('N', 'N', m, l, l, 1.0, Q, ldq, Uhat.p, l, 0.0, U, ldu);                      // U = Q Uhat (:286)
     copy_matrix(Uhat.p, l, X.p, l, l, l);
     scale_cols(X.p, l, l, l, S, 1);                                                  // Uhat S^{-1} (:293-295)
     mm('N', 'N', n, l, l, 1.0, Bt.p, n, X.p, l, 0.0, V, ldv);                        // V = B^T Uhat S^{-1} (:296)
     return g_status;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Deterministic baselines and legacy entry points
+// ---------------------------------------------------------------------------------------------------------
+// Full SVD behind low_rank_svd_decomp_fixed_rank_or_prec (RRA:7-69: dgesvd 'S','S' on a copy, then truncation by the
+// caller).  A (m x n) = U diag(S) V^T with r = min(m,n): U m x r, S r descending, V n x r.  The tall orientation is
+// QR-factored (CholeskyQR2, TSQR fallback) and the r x r triangular factor goes through the one-sided Jacobi kernel.
+int svd_full(const double *A, i64 m, i64 n, i64 lda, double *U, i64 ldu, double *S, double *V, i64 ldv) {
+    ensure_init();
+    Ctx &c = ctx();
+    if (!c.inited) return 1;
+    const i64 r = min(m, n), t = max(m, n);
+    if (r <= 0) return g_status;
+    DBuf W((size_t)t * r), R((size_t)r * r), Uh((size_t)r * r), Vt((size_t)r * r);
+    if (m >= n) copy_matrix(A, lda, W.p, t, m, n);
+    else transpose(A, lda, W.p, t, m, n);                                  // W = A^T (n x m)
+    orthonormalize(W.p, t, t, r, R.p, r, /*sharded=*/false);               // W = Qw, R upper
+    jacobi_svd(R.p, r, r, Uh.p, r, S, Vt.p, r);                            // R = Uh S Vt
+    if (m >= n) {                                                          // A = (Qw Uh) S Vt
+        mm('N', 'N', m, r, r, 1.0, W.p, t, Uh.p, r, 0.0, U, ldu);
+        transpose(Vt.p, r, V, ldv, r, r);
+    } else {                                                               // A^T = (Qw Uh) S Vt  =>  A = Vt^T S (Qw Uh)^T
+        mm('N', 'N', n, r, r, 1.0, W.p, t, Uh.p, r, 0.0, V, ldv);
+        transpose(Vt.p, r, U, ldu, r, r);
+    }
+    return g_status;
+}
+
+// randQB_p (RRA:1343-1421): single-vector randQB with p power steps.  A (m x n) is destroyed (the reference deflates a
+// private copy).  The reference's sequential projection loop runs over i < j-1 (it skips the newest column); it is applied
+// here as one classical Gram-Schmidt pass over the same columns — the coefficients are O(eps) because A is deflated.
+int randqb_single(double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, uint64_t seed, double *Q, i64 ldq, double *B, i64 ldb) {
+    ensure_init();
+    Ctx &c = ctx();
+    if (!c.inited) return 1;
+    if (k <= 0 || p < 0) { set_error("rsvd_b200: randQB_p needs k > 0 and p >= 0"); return 1; }
+    DBuf r((size_t)n), y((size_t)m), pj((size_t)n), cj((size_t)k), nrm(1);
+    for (i64 j = 0; j < k; ++j) {
+        fill_normal(r.p, n, seed, j * n);                                  // RN(:, j), RN n x k column-major (RRA:1350,1377)
+        gemv('N', m, n, 1.0, A, lda, r.p, 0.0, y.p);                       // yj = A rj
+        for (i64 i = 0; i < p; ++i) {
+            gemv('T', m, n, 1.0, A, lda, y.p, 0.0, pj.p);
+            gemv('N', m, n, 1.0, A, lda, pj.p, 0.0, y.p);
+        }
+        if (j - 1 > 0) {                                                   // i < j-1 (RRA:1387)
+            gemv('T', m, j - 1, 1.0, Q, ldq, y.p, 0.0, cj.p);
+            gemv('N', m, j - 1, -1.0, Q, ldq, cj.p, 1.0, y.p);
+        }
+        double *qj = Q + j * ldq;
+        sumsq_async(y.p, m, m, 1, nrm.p);
+        scale_by_inv_norm(y.p, m, nrm.p, qj);                              // qj = yj / ||yj||
+        gemv('T', m, n, 1.0, A, lda, qj, 0.0, pj.p);                       // bj = A^T qj
+        copy_matrix(pj.p, 1, B + j, ldb, 1, n);                            // B(j, :) = bj
+        rank1_update(A, lda, m, n, qj, pj.p);                              // A -= qj bj^T
+        if (g_status) break;
+    }
+    return g_status;
+}
+
+// estimate_rank_and_buildQ (MVF:1339-1400): Y = A RN with RN n x maxdim, sequential modified Gram-Schmidt over the columns
+// with the reference's stop rule (two consecutive projections shorter than TOL), then an orthonormal basis of the first
+// good_rank columns.  Q: m x maxdim buffer, the first *rank_out columns are the result.
+int estimate_rank1(const double *A, i64 m, i64 n, i64 lda, i64 maxdim, double tol, uint64_t seed, double *Q, i64 ldq, i64 *rank_out) {
+    ensure_init();
+    Ctx &c = ctx();
+    if (!c.inited) return 1;
+    *rank_out = 0;
+    if (maxdim <= 0 || maxdim > n) { set_error("rsvd_b200: estimate_rank_and_buildQ needs 0 < maxdim <= n (got %lld)", (long long)maxdim); return 1; }
+    sketch('N', m, maxdim, n, A, lda, seed, 1, n, 0, Q, ldq);
+    const i64 good = mgs_rank_estimate(Q, ldq, m, maxdim, tol);
+    if (good < 0 || g_status) return 1;
+    if (good > 0) orthonormalize(Q, ldq, m, good, nullptr, 0, false);   // QR_factorization_getQ(Qsmall) (MVF:1393)
+    *rank_out = good;
+    return g_status;
+}
+
+// estimate_rank_and_buildQ2 (MVF:1404-1467): grow Y = A [RN_0 RN_1 ...] by kblock columns until
+// ||Q Q^T A - A||_F / ||Q Q^T A||_F <= tol (get_percent_error_between_two_mats(QQtM, M)/100).  The reference reseeds each
+// RN_b with time(NULL), i.e. draws the SAME block again within one second; here block b continues the Philox stream
+// (columns b*kblock.. of one wide RN), which is what the algorithm intends.  Stops at max_cols.
+int estimate_rank2(const double *A, i64 m, i64 n, i64 lda, i64 kblock, double tol, uint64_t seed, double *Y, i64 ldy, double *Q, i64 ldq,
+                   i64 max_cols, i64 *rank_out) {
+    ensure_init();
+    Ctx &c = ctx();
+    if (!c.inited) return 1;
+    *rank_out = 0;
+    if (kblock <= 0 || kblock > max_cols) { set_error("rsvd_b200: estimate_rank_and_buildQ2 needs 0 < kblock <= min(m,n)"); return 1; }
+    DBuf Res((size_t)m * n), sums(2);
+    i64 cols = 0;
+    for (;;) {
+        sketch('N', m, kblock, n, A, lda, seed, 1, n, cols * n, Y + cols * ldy, ldy);
+        cols += kblock;
+        copy_matrix(Y, ldy, Q, ldq, m, cols);
+        orthonormalize(Q, ldq, m, cols, nullptr, 0, false);
+        DBuf B((size_t)cols * n);
+        mm('T', 'N', cols, n, m, 1.0, Q, ldq, A, lda, 0.0, B.p, cols);
+        copy_matrix(A, lda, Res.p, m, m, n);
+        mm('N', 'N', m, n, cols, -1.0, Q, ldq, B.p, cols, 1.0, Res.p, m);
+        sumsq_async(Res.p, m, m, n, sums.p);
+        sumsq_async(B.p, cols, cols, n, sums.p + 1);
+        double h[2] = {0, 0};
+        RSVD_CUDA(cudaMemcpyAsync(h, sums.p, 16, cudaMemcpyDeviceToHost, c.stream));
+        RSVD_CUDA(cudaStreamSynchronize(c.stream));
+        if (g_status) return 1;
+        const double err = sqrt(h[0]) / sqrt(h[1]);
+        if (c.verbose) fprintf(stderr, "[rsvd_b200] estimate_rank2: %lld columns, error_norm = %g\n", (long long)cols, err);
+        if (!(err > tol) || cols + kblock > max_cols) break;
+    }
+    *rank_out = cols;
+    return g_status;
+}
+
+// power iterations + SVD tail from an existing sketch Y (m x l, destroyed): randomized_low_rank_svd3_autorank2 (RRA:826-918)
+int svd_rand_from_sketch(const double *A, i64 m, i64 n, i64 lda, double *Y, i64 ldy, i64 l, int q, int s, double *U, i64 ldu,
+                         double *S, double *V, i64 ldv) {
+    DBuf Y0((size_t)m * l);
+    copy_matrix(Y, ldy, Y0.p, m, m, l);
+    return svd_rand_impl(A, m, n, lda, l, 0, 1, q, s, 0, nullptr, &Y0, U, ldu, S, V, ldv);
 }
 
 // streamed 100*||A - U diag(S) V^T||_F / ||A||_F

@@ -347,4 +347,132 @@ __global__ void __launch_bounds__(1024) lu_factor_kernel(double *A, i64 lda, int
     }
 }
 
+
+// ---- BLAS-2 pieces of the single-vector randQB (HBM-bound: every call streams A once) ----------------------------
+// y = alpha * A x + beta * y : one thread per row, columns split over gridDim.y into partial sums that are reduced in a
+// fixed order (deterministic)
+__global__ void gemv_n_partial_kernel(const double *__restrict__ A, i64 lda, i64 m, i64 n, const double *__restrict__ x, double *part) {
+    const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const i64 chunk = (n + gridDim.y - 1) / gridDim.y;
+    const i64 j0 = (i64)blockIdx.y * chunk, j1 = min(n, j0 + chunk);
+    double acc = 0.0;
+    for (i64 j = j0; j < j1; ++j) acc = fma(A[j * lda + r], x[j], acc);
+    part[(i64)blockIdx.y * m + r] = acc;
+}
+__global__ void gemv_n_reduce_kernel(const double *__restrict__ part, i64 m, int chunks, double alpha, double beta, double *y) {
+    const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    double acc = 0.0;
+    for (int c = 0; c < chunks; ++c) acc += part[(i64)c * m + r];
+    y[r] = alpha * acc + (beta != 0.0 ? beta * y[r] : 0.0);
+}
+// y = alpha * A^T x + beta * y : one warp per column
+__global__ void gemv_t_kernel(const double *__restrict__ A, i64 lda, i64 m, i64 n, const double *__restrict__ x, double alpha, double beta, double *y) {
+    const int lane = threadIdx.x & 31;
+    i64 w = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 j = w; j < n; j += nw) {
+        const double *col = A + j * lda;
+        double acc = 0.0;
+        for (i64 r = lane; r < m; r += 32) acc = fma(col[r], x[r], acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) y[j] = alpha * acc + (beta != 0.0 ? beta * y[j] : 0.0);
+    }
+}
+void gemv(char trans, i64 m, i64 n, double alpha, const double *A, i64 lda, const double *x, double beta, double *y) {
+    if (g_status || m <= 0 || n <= 0) return;
+    Ctx &c = ctx();
+    if (trans == 'N') {
+        const int bx = (int)((m + 255) / 256);
+        int chunks = (int)max((i64)1, min((i64)64, min(n / 32, (i64)(c.sms * 8) / bx)));
+        DBuf part((size_t)chunks * m);
+        gemv_n_partial_kernel<<<dim3(bx, chunks), 256, 0, c.stream>>>(A, lda, m, n, x, part.p);
+        gemv_n_reduce_kernel<<<bx, 256, 0, c.stream>>>(part.p, m, chunks, alpha, beta, y);
+        count_launch(2);
+    } else {
+        const int blocks = (int)max((i64)1, min((i64)c.sms * 8, (n + 7) / 8));
+        gemv_t_kernel<<<blocks, 256, 0, c.stream>>>(A, lda, m, n, x, alpha, beta, y);
+        count_launch();
+    }
+}
+__global__ void rank1_update_kernel(double *A, i64 lda, i64 m, i64 n, const double *__restrict__ q, const double *__restrict__ b) {
+    const i64 total = m * n;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 r = e % m, j = e / m;
+        A[j * lda + r] = fma(-q[r], b[j], A[j * lda + r]);
+    }
+}
+void rank1_update(double *A, i64 lda, i64 m, i64 n, const double *q, const double *b) {
+    if (g_status || m <= 0 || n <= 0) return;
+    rank1_update_kernel<<<grid_for(m * n), 256, 0, ctx().stream>>>(A, lda, m, n, q, b);
+    count_launch();
+}
+__global__ void scale_by_inv_norm_kernel(const double *__restrict__ y, i64 m, const double *__restrict__ sumsq, double *q) {
+    const double inv = 1.0 / sqrt(sumsq[0]);
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (i64)gridDim.x * blockDim.x) q[e] = y[e] * inv;
+}
+void scale_by_inv_norm(const double *y, i64 m, const double *sumsq, double *q) {
+    if (g_status || m <= 0) return;
+    scale_by_inv_norm_kernel<<<grid_for(m), 256, 0, ctx().stream>>>(y, m, sumsq, q);
+    count_launch();
+}
+
+
+// Sequential modified Gram-Schmidt with the stop rule of estimate_rank_and_buildQ (MVF:1366-1388): column j is projected
+// against the finished columns one at a time; when two consecutive projections (the second may belong to the previous
+// column: p1 persists across j) are both shorter than tol the scan stops and j is the rank.  One CTA: the loop is a chain of
+// dependent dot products.
+__global__ void __launch_bounds__(1024) mgs_rank_kernel(double *Q, i64 ldq, i64 m, i64 maxdim, double tol, int *rank_out) {
+    __shared__ double sh[2 * 32];
+    __shared__ double bc[2];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    double p1norm = 0.0;
+    int good = (int)maxdim;
+    for (i64 j = 0; j < maxdim; ++j) {
+        double *vj = Q + j * ldq;
+        bool stop = false;
+        for (i64 i = 0; i < j; ++i) {
+            const double *vi = Q + i * ldq;
+            double d = 0.0, u = 0.0;
+            for (i64 r = tid; r < m; r += nt) { const double a = vi[r]; d = fma(vj[r], a, d); u = fma(a, a, u); }
+            for (int o = 16; o > 0; o >>= 1) { d += __shfl_xor_sync(0xffffffffu, d, o); u += __shfl_xor_sync(0xffffffffu, u, o); }
+            if (lane == 0) { sh[2 * wid] = d; sh[2 * wid + 1] = u; }
+            __syncthreads();
+            if (tid == 0) {
+                double dd = 0.0, uu = 0.0;
+                for (int w = 0; w < (nt >> 5); ++w) { dd += sh[2 * w]; uu += sh[2 * w + 1]; }
+                bc[0] = dd / uu; bc[1] = sqrt(uu);
+            }
+            __syncthreads();
+            const double coef = bc[0], pnorm = fabs(coef) * bc[1];
+            for (i64 r = tid; r < m; r += nt) vj[r] = fma(-coef, vi[r], vj[r]);
+            __syncthreads();
+            if (pnorm < tol && p1norm < tol) { good = (int)j; stop = true; break; }
+            p1norm = pnorm;
+        }
+        if (stop) break;
+        double u = 0.0;
+        for (i64 r = tid; r < m; r += nt) u = fma(vj[r], vj[r], u);
+        for (int o = 16; o > 0; o >>= 1) u += __shfl_xor_sync(0xffffffffu, u, o);
+        if (lane == 0) sh[wid] = u;
+        __syncthreads();
+        if (tid == 0) { double uu = 0.0; for (int w = 0; w < (nt >> 5); ++w) uu += sh[w]; bc[0] = 1.0 / sqrt(uu); }
+        __syncthreads();
+        const double inv = bc[0];
+        for (i64 r = tid; r < m; r += nt) vj[r] *= inv;
+        __syncthreads();
+    }
+    if (tid == 0) *rank_out = good;
+}
+i64 mgs_rank_estimate(double *Q, i64 ldq, i64 m, i64 maxdim, double tol) {
+    if (g_status) return -1;
+    Ctx &c = ctx();
+    mgs_rank_kernel<<<1, 1024, 0, c.stream>>>(Q, ldq, m, maxdim, tol, c.d_flag + 28);
+    count_launch();
+    RSVD_CUDA(cudaMemcpyAsync(c.h_flag + 28, c.d_flag + 28, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    RSVD_CUDA(cudaStreamSynchronize(c.stream));
+    return g_status ? -1 : (i64)c.h_flag[28];
+}
+
 }  // namespace rsvd

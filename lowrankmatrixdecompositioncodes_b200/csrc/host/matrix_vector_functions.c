@@ -403,18 +403,26 @@ static void host_qr(mat *M, mat *Q, mat *R) {
 void compact_QR_factorization(mat *M, mat *Q, mat *R) { host_qr(M, Q, R); }
 void QR_factorization_getQ(mat *M, mat *Q) { host_qr(M, Q, NULL); }
 
+/* MVF:1270-1284 (dgesvd 'S','S'): U m x r, S r x r diagonal, Vt r x n, r = min(m,n).  Square inputs (the hot path's l x l
+ * Rhat) go straight to the Jacobi kernel; other shapes through the QR-preconditioned full SVD. */
 void singular_value_decomposition(mat *M, mat *U, mat *S, mat *Vt) {
-    idx_t m = M->nrows, n = M->ncols;
-    if (m != n) { rsvd_api_error("singular_value_decomposition: only square inputs are on the hot path (got %lld x %lld)", (long long)m, (long long)n); return; }
-    double *dA = rsvd_upload(M->d, (size_t)n * (size_t)n);
-    double *dU = rsvd_b200_dev_alloc((rsvd_i64)n * n + 1), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * n + 1), *ds = rsvd_b200_dev_alloc(n + 1);
+    idx_t m = M->nrows, n = M->ncols, r = min(m, n);
+    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dU = rsvd_b200_dev_alloc((rsvd_i64)m * r + 1), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * r + 1), *ds = rsvd_b200_dev_alloc(r + 1);
     if (dA && dU && dV && ds) {
-        rsvd_b200_svd_small(dA, n, n, dU, n, ds, dV, n);
-        rsvd_download(U->d, dU, (size_t)n * (size_t)n);
-        rsvd_download(Vt->d, dV, (size_t)n * (size_t)n);
-        double *s = (double *)malloc((size_t)(n ? n : 1) * sizeof(double));
-        rsvd_download(s, ds, (size_t)n);
-        for (idx_t i = 0; i < n; ++i) EL(S, i, i) = s[i];
+        if (m == n) {
+            rsvd_b200_svd_small(dA, n, n, dU, n, ds, dV, n);                  /* dV holds V^T */
+            rsvd_download(Vt->d, dV, (size_t)n * (size_t)n);
+        } else {
+            rsvd_b200_svd_full_dev(dA, m, n, m, dU, m, ds, dV, n);            /* dV holds V (n x r) */
+            double *dVt = rsvd_b200_dev_alloc((rsvd_i64)n * r + 1);
+            if (dVt) { rsvd_b200_transpose(dV, n, dVt, r, n, r); rsvd_download(Vt->d, dVt, (size_t)n * (size_t)r); }
+            rsvd_b200_dev_free(dVt);
+        }
+        rsvd_download(U->d, dU, (size_t)m * (size_t)r);
+        double *s = (double *)malloc((size_t)(r ? r : 1) * sizeof(double));
+        rsvd_download(s, ds, (size_t)r);
+        for (idx_t i = 0; i < r; ++i) EL(S, i, i) = s[i];
         free(s);
     }
     rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dV); rsvd_b200_dev_free(ds);
@@ -457,6 +465,57 @@ void square_matrix_system_solve(mat *A, mat *X, mat *B) {
         matrix_copy(X, B);
     }
     rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dB);
+    rsvd_api_sync_error();
+}
+
+/* ---- legacy range-finder helpers (MVF:795-841, 1339-1467) ------------------------------------------ */
+/* p = (v.u / ||u||^2) u   (MVF:795-802) */
+void project_vector(vec *v, vec *u, vec *p) {
+    double nu = vector_get2norm(u);
+    double c = vector_dot_product(v, u) / (nu * nu);
+    vector_copy(p, u);
+    vector_scale(p, c);
+}
+
+/* MVF:817-841: two passes of modified Gram-Schmidt = the QR factor with positive diagonal R, which is what the
+ * CholeskyQR2 device kernel returns. */
+void build_orthonormal_basis_from_mat(mat *A, mat *Q) { host_qr(A, Q, NULL); }
+
+/* MVF:1339-1400 */
+void estimate_rank_and_buildQ(mat *M, double frac_of_max_rank, double TOL, mat **Q, idx_t *good_rank) {
+    idx_t m = M->nrows, n = M->ncols;
+    idx_t maxdim = (idx_t)llround((double)min(m, n) * frac_of_max_rank);
+    *Q = NULL; *good_rank = 0;
+    if (maxdim <= 0 || maxdim > min(m, n)) { rsvd_api_error("estimate_rank_and_buildQ: frac_of_max_rank must give 0 < maxdim <= min(m,n)"); *Q = matrix_new(m, 0); return; }
+    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dQ = rsvd_b200_dev_alloc((rsvd_i64)m * maxdim + 1);
+    rsvd_i64 rank = 0;
+    if (dA && dQ) rsvd_b200_estimate_rank1_dev(dA, m, n, m, maxdim, TOL, (uint64_t)rsvd_b200_get_option("seed"), dQ, m, &rank);
+    rsvd_b200_dev_free(dA);
+    *good_rank = (idx_t)rank;
+    *Q = matrix_new(m, *good_rank);
+    if (dQ) rsvd_download((*Q)->d, dQ, (size_t)m * (size_t)*good_rank);
+    rsvd_b200_dev_free(dQ);
+    rsvd_api_sync_error();
+}
+
+/* MVF:1404-1467 */
+void estimate_rank_and_buildQ2(mat *M, idx_t kblock, double TOL, mat **Y, mat **Q, idx_t *good_rank) {
+    idx_t m = M->nrows, n = M->ncols, r = min(m, n);
+    *Y = NULL; *Q = NULL; *good_rank = 0;
+    if (kblock <= 0 || kblock > r) { rsvd_api_error("estimate_rank_and_buildQ2: need 0 < kblock <= min(m,n)"); *Y = matrix_new(m, 0); *Q = matrix_new(m, 0); return; }
+    idx_t cap = (r / kblock) * kblock;
+    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dY = rsvd_b200_dev_alloc((rsvd_i64)m * cap + 1), *dQ = rsvd_b200_dev_alloc((rsvd_i64)m * cap + 1);
+    rsvd_i64 rank = 0;
+    if (dA && dY && dQ)
+        rsvd_b200_estimate_rank2_dev(dA, m, n, m, kblock, TOL, (uint64_t)rsvd_b200_get_option("seed"), dY, m, dQ, m, cap, &rank);
+    rsvd_b200_dev_free(dA);
+    *good_rank = (idx_t)rank;
+    *Y = matrix_new(m, *good_rank); *Q = matrix_new(m, *good_rank);
+    if (dY) rsvd_download((*Y)->d, dY, (size_t)m * (size_t)*good_rank);
+    if (dQ) rsvd_download((*Q)->d, dQ, (size_t)m * (size_t)*good_rank);
+    rsvd_b200_dev_free(dY); rsvd_b200_dev_free(dQ);
     rsvd_api_sync_error();
 }
 

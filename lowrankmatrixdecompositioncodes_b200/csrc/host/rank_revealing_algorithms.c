@@ -230,20 +230,79 @@ void id_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t q, idx_t s, vec *
     rsvd_api_sync_error();
 }
 
-/* RRA:1807-1854.  Only the branch the hot path reaches (k == min(m,n): full dgeqp3, RRA:1830-1834) is on the device;
- * the partial-rank Householder branch (RRA:1828-1829) is a deterministic baseline outside the north-star path. */
+/* Runs the reference's own partial pivoted QR on the device and leaves I, R (kmax x n, ld kmax) there.  Returns frank. */
+static idx_t pqr_device(mat *M, idx_t k, double TOL, int zero_exact, double **dI_out, double **dQ_out, double **dR_out, idx_t *kmax_out) {
+    idx_t m = M->nrows, n = M->ncols, r = min(m, n);
+    idx_t kmax = (k <= 0) ? r : min(k, r);
+    double *dW = rsvd_upload(M->d, (size_t)m * (size_t)n);          /* the private copy R = M (RRA:1192) */
+    double *dI = rsvd_b200_dev_alloc(n + 1);
+    double *dQ = dQ_out ? rsvd_b200_dev_alloc((rsvd_i64)m * kmax + 1) : NULL;
+    double *dR = rsvd_b200_dev_alloc((rsvd_i64)kmax * n + 1);
+    rsvd_i64 fr = 0;
+    if (dW && dI && dR && (!dQ_out || dQ))
+        rsvd_b200_pqr_partial_dev(dW, m, m, n, k, TOL, zero_exact, dI, dQ, m, dR, kmax, &fr);
+    rsvd_b200_dev_free(dW);
+    *dI_out = dI; if (dQ_out) *dQ_out = dQ; *dR_out = dR; *kmax_out = kmax;
+    rsvd_api_sync_error();
+    return (idx_t)fr;
+}
+
+static void pqr_host(mat *M, idx_t k, double TOL, int zero_exact, const char *who, idx_t *frank, mat **Qk, mat **Rk, vec **I) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols, kmax = 0;
+    if (k > min(m, n)) rsvd_api_error("%s: k = %lld exceeds min(m,n) = %lld; clamped", who, (long long)k, (long long)min(m, n));
+    double *dI = NULL, *dQ = NULL, *dR = NULL;
+    *frank = pqr_device(M, k, TOL, zero_exact, &dI, &dQ, &dR, &kmax);
+    *I = download_vec(dI, n);
+    *Qk = matrix_new(m, *frank);
+    if (dQ) rsvd_download((*Qk)->d, dQ, (size_t)m * (size_t)*frank);
+    *Rk = download_mat(dR, kmax, n);
+    if (*frank != kmax) resize_matrix_by_rows(Rk, *frank);
+    rsvd_b200_dev_free(dI); rsvd_b200_dev_free(dQ); rsvd_b200_dev_free(dR);
+    rsvd_api_sync_error();
+}
+
+/* RRA:1012-1155 (stops on an exactly zero pivot norm) and RRA:1159-1334 (|norm^2| < 1e-10, or R22norm < TOL when k <= 0) */
+void pivoted_QR_of_specified_rank(mat *M, idx_t k, idx_t *frank, mat **Qk, mat **Rk, vec **I) {
+    if (k <= 0) { rsvd_api_begin(); rsvd_api_error("pivoted_QR_of_specified_rank: need k > 0"); *frank = 0; *Qk = matrix_new(M->nrows, 0); *Rk = matrix_new(0, M->ncols); *I = vector_new(M->ncols); return; }
+    pqr_host(M, k, 0.0, 1, "pivoted_QR_of_specified_rank", frank, Qk, Rk, I);
+}
+void pivoted_QR_of_specified_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, mat **Qk, mat **Rk, vec **I) {
+    pqr_host(M, k, TOL, 0, "pivoted_QR_of_specified_rank_or_prec", frank, Qk, Rk, I);
+}
+
+/* RRA:982-1008: H(ind1:ind2) = x(ind1:ind2), H(ind1) -= ||x(ind1:ind2)||, scaled so that I - H H^T is the reflector. */
+void get_householder_matrix(vec *x, idx_t ind1, idx_t ind2, mat *H) {
+    double nrm = 0.0;
+    for (idx_t i = ind1; i < ind2; ++i) { H->d[i] = x->d[i]; nrm += x->d[i] * x->d[i]; }
+    H->d[ind1] -= sqrt(nrm);
+    double val = get_matrix_frobenius_norm(H);
+    if (val > 0) matrix_scale(H, sqrt(2.0 / (val * val)));
+}
+
+/* RRA:1807-1854.  k == min(m,n): full dgeqp3-rule pivoted QR (the branch the randomized hot path reaches, RRA:1830-1834);
+ * k < min(m,n) or k <= 0: the reference's own partial Householder QR in rank or tolerance mode (RRA:1828-1829). */
 void id_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, vec **I, mat **T) {
-    (void)TOL;
     rsvd_api_begin();
     idx_t m = M->nrows, n = M->ncols;
     *I = NULL; *T = NULL;
-    if (k < min(m, n) || k <= 0) {
-        rsvd_api_error("id_decomp_fixed_rank_or_prec: only k == min(m,n) (full pivoted QR) is implemented (k=%lld, M %lld x %lld)",
-                       (long long)k, (long long)m, (long long)n);
-        *I = vector_new(n); *T = matrix_new(max(k, 0), max(n - k, 0));
+    if (k < min(m, n)) {
+        idx_t kmax = 0;
+        double *dI = NULL, *dR = NULL;
+        idx_t f = pqr_device(M, k, TOL, 0, &dI, NULL, &dR, &kmax);
+        *frank = f;
+        *I = download_vec(dI, n);
+        if (f > 0 && n > f && dR) rsvd_b200_trsm_left_upper(dR, kmax, f, dR + (size_t)f * kmax, kmax, n - f);   /* T = triu(Rk1)^{-1} Rk2 */
+        mat *Tfull = matrix_new(kmax, n - f);
+        if (dR && n > f) rsvd_download(Tfull->d, dR + (size_t)f * kmax, (size_t)kmax * (size_t)(n - f));
+        if (f != kmax) resize_matrix_by_rows(&Tfull, f);
+        *T = Tfull;
+        rsvd_b200_dev_free(dI); rsvd_b200_dev_free(dR);
+        rsvd_api_sync_error();
         return;
     }
     if (m > n) { rsvd_api_error("id_decomp_fixed_rank_or_prec: need nrows <= ncols"); *I = vector_new(n); *T = matrix_new(k, 0); return; }
+    k = min(m, n);
     *frank = k;
     double *dM = rsvd_upload(M->d, (size_t)m * (size_t)n);
     double *dI = rsvd_b200_dev_alloc(n + 1), *dT = rsvd_b200_dev_alloc((rsvd_i64)k * (n - k) + 1);
@@ -253,6 +312,41 @@ void id_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, vec
     *T = download_mat(dT, k, n - k);
     rsvd_b200_dev_free(dI); rsvd_b200_dev_free(dT);
     rsvd_api_sync_error();
+}
+
+/* RRA:2034-2056: column ID of M, then the (full) row ID of M(:, Icol(1:frank))^T */
+void id_two_sided_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, vec **Icol, vec **Irow, mat **T, mat **S) {
+    idx_t m = M->nrows;
+    id_decomp_fixed_rank_or_prec(M, k, TOL, frank, Icol, T);
+    if (g_api_status) { *Irow = vector_new(m); *S = matrix_new(*frank, m - *frank); return; }
+    mat *MI = matrix_new(m, *frank), *MIt = matrix_new(*frank, m);
+    fill_matrix_from_first_columns_from_list(M, *Icol, *frank, MI);
+    matrix_build_transpose(MIt, MI);
+    id_decomp_fixed_rank_or_prec(MIt, *frank, 0, frank, Irow, S);
+    matrix_delete(MI); matrix_delete(MIt);
+}
+
+/* RRA:2115-2187: two-sided ID, then the same CUR tail as cur_rand_decomp_fixed_rank (device: rsvd_b200_cur_from_id_dev) */
+void cur_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, mat **C, mat **U, mat **R) {
+    idx_t m = M->nrows, n = M->ncols;
+    vec *Icol = NULL, *Irow = NULL;
+    mat *T = NULL, *S = NULL;
+    *C = NULL; *U = NULL; *R = NULL;
+    id_two_sided_decomp_fixed_rank_or_prec(M, k, TOL, frank, &Icol, &Irow, &T, &S);
+    k = *frank;                                                      /* RRA:2125-2127 (k <= 0) — and the only consistent size otherwise */
+    if (g_api_status || k <= 0) {
+        *C = matrix_new(m, max(k, 0)); *U = matrix_new(max(k, 0), max(k, 0)); *R = matrix_new(max(k, 0), n);
+    } else {
+        double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
+        double *dIc = rsvd_upload(Icol->d, (size_t)n), *dIr = rsvd_upload(Irow->d, (size_t)m), *dT = rsvd_upload(T->d, (size_t)k * (size_t)(n - k));
+        double *dC = rsvd_b200_dev_alloc((rsvd_i64)m * k + 1), *dU = rsvd_b200_dev_alloc((rsvd_i64)k * k + 1), *dR = rsvd_b200_dev_alloc((rsvd_i64)k * n + 1);
+        if (dA && dIc && dIr && dT && dC && dU && dR) rsvd_b200_cur_from_id_dev(dA, m, n, m, dIc, dIr, dT, k, k, dC, m, dU, k, dR, k);
+        rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dIc); rsvd_b200_dev_free(dIr); rsvd_b200_dev_free(dT);
+        *C = download_mat(dC, m, k); *U = download_mat(dU, k, k); *R = download_mat(dR, k, n);
+        rsvd_b200_dev_free(dC); rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dR);
+        rsvd_api_sync_error();
+    }
+    vector_delete(Icol); vector_delete(Irow); matrix_delete(T); matrix_delete(S);
 }
 
 void id_two_sided_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t q, idx_t s, vec **Icol, vec **Irow, mat **T, mat **S) {
@@ -494,4 +588,159 @@ void use_cur_decomp_for_approximation(mat *M, mat *C, mat *U, mat *R) {
     form_cur_product_matrix(C, U, R, P);
     report(M, P, "C U R");
     matrix_delete(P);
+}
+
+/* M(:, I) ~ Qk Rk  (RRA:2351-2384).  Deliberate deviation: the reference also frees the CALLER's Qk and Rk here (RRA:2378) and
+ * its own driver 4 frees them again at exit (driver_multi_core_mkl4.c:139, a double free); the inputs are left alone. */
+void use_pivoted_QR_decomp_for_approximation(mat *M, mat *Qk, mat *Rk, vec *I) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols;
+    mat *QR = matrix_new(m, n), *P = matrix_new(m, n);
+    matrix_matrix_mult(Qk, Rk, QR);
+    for (idx_t j = 0; j < n; ++j) memcpy(&P->d[(size_t)((idx_t)I->d[j]) * m], &QR->d[(size_t)j * m], (size_t)m * sizeof(double));
+    g_last_percent_error = get_percent_error_between_two_mats(M, P);
+    printf("percent_error between M and QkRkPt = %f\n", g_last_percent_error);
+    matrix_delete(QR); matrix_delete(P);
+}
+
+/* ---- deterministic SVD baseline (RRA:7-69) ---------------------------------------------------------------------------
+ * Tolerance mode keeps the reference's integer abs(): `abs(sval) < TOL` truncates sval to int first (RRA:49), so the rank
+ * is the first i with |trunc(sigma_i)| < TOL. */
+void low_rank_svd_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, mat **U, mat **S, mat **V) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols, r = min(m, n);
+    int tolMode = (k <= 0);
+    if (tolMode) k = r;
+    if (k > r) { rsvd_api_error("low_rank_svd_decomp_fixed_rank_or_prec: k = %lld exceeds min(m,n) = %lld; clamped", (long long)k, (long long)r); k = r; }
+    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dU = rsvd_b200_dev_alloc((rsvd_i64)m * r + 1), *dS = rsvd_b200_dev_alloc(r + 1), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * r + 1);
+    if (dA && dU && dS && dV) rsvd_b200_svd_full_dev(dA, m, n, m, dU, m, dS, dV, n);
+    rsvd_b200_dev_free(dA);
+    *frank = k;
+    if (tolMode && dS) {
+        double *sv = (double *)malloc((size_t)(r ? r : 1) * sizeof(double));
+        rsvd_download(sv, dS, (size_t)r);
+        for (idx_t i = 0; i < r; ++i)
+            if ((double)labs((long)sv[i]) < TOL && i < r - 1) { *frank = i + 1; break; }
+        free(sv);
+    }
+    *U = download_mat(dU, m, *frank);
+    *S = diag_from_device(dS, *frank);
+    *V = download_mat(dV, n, *frank);
+    rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dS); rsvd_b200_dev_free(dV);
+    rsvd_api_sync_error();
+}
+
+/* ---- legacy randomized SVD entry points (RRA:385-918): re-sequencings of the kernels above ------------------------- */
+/* RRA:385-461 = eig(B B^T) variant without oversampling or power iterations */
+void randomized_low_rank_svd1(mat *M, idx_t k, mat **U, mat **S, mat **V) {
+    idx_t fr = 0;
+    low_rank_svd_rand_decomp_fixed_rank(M, k, 0, 2, 1, 1, &fr, U, S, V);
+}
+/* RRA:465-532 = QR/SVD variant without oversampling or power iterations */
+void randomized_low_rank_svd2(mat *M, idx_t k, mat **U, mat **S, mat **V) {
+    idx_t fr = 0;
+    low_rank_svd_rand_decomp_fixed_rank(M, k, 0, 1, 1, 1, &fr, U, S, V);
+}
+/* RRA:536-634 = QR/SVD variant with the (M M^T)^(q-1) M power scheme, loop j < q */
+void randomized_low_rank_svd3(mat *M, idx_t k, idx_t q, idx_t s, mat **U, mat **S, mat **V) {
+    idx_t fr = 0;
+    low_rank_svd_rand_decomp_fixed_rank(M, k, 0, 1, q, s, &fr, U, S, V);
+}
+
+/* RRA:1425-1572 */
+static int randqb_pb_device(mat *M, idx_t kstep, idx_t nstep, idx_t p, idx_t s, double **dQ_out, double **dB_out) {
+    idx_t m = M->nrows, n = M->ncols, l = kstep * nstep;
+    *dQ_out = NULL; *dB_out = NULL;
+    if (kstep <= 0 || nstep <= 0 || s <= 0 || p < 0 || l > min(m, n)) { rsvd_api_error("randQB_pb: need kstep, nstep, s > 0, p >= 0 and kstep*nstep <= min(m,n)"); return 1; }
+    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dQ = rsvd_b200_dev_alloc((rsvd_i64)m * l + 1), *dB = rsvd_b200_dev_alloc((rsvd_i64)l * n + 1);
+    if (dA && dQ && dB) rsvd_b200_randqb_legacy_dev(dA, m, n, m, kstep, nstep, (int)p, (int)s, omega_seed(), dQ, m, dB, l);
+    rsvd_b200_dev_free(dA);
+    *dQ_out = dQ; *dB_out = dB;
+    rsvd_api_sync_error();
+    return g_api_status;
+}
+void randQB_pb(mat *M, idx_t kstep, idx_t nstep, idx_t p, idx_t s, mat **Q, mat **B) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols, l = max(kstep, 0) * max(nstep, 0);
+    double *dQ = NULL, *dB = NULL;
+    if (randqb_pb_device(M, kstep, nstep, p, s, &dQ, &dB)) { *Q = matrix_new(m, l); *B = matrix_new(l, n); }
+    else { *Q = download_mat(dQ, m, l); *B = download_mat(dB, l, n); }
+    rsvd_b200_dev_free(dQ); rsvd_b200_dev_free(dB);
+    rsvd_api_sync_error();
+}
+
+/* RRA:1343-1421 */
+void randQB_p(mat *M, idx_t k, idx_t p, mat **Q, mat **B) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols;
+    if (k <= 0 || p < 0 || k > min(m, n)) { rsvd_api_error("randQB_p: need 0 < k <= min(m,n) and p >= 0"); *Q = matrix_new(m, max(k, 0)); *B = matrix_new(max(k, 0), n); return; }
+    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dQ = rsvd_b200_dev_alloc((rsvd_i64)m * k + 1), *dB = rsvd_b200_dev_alloc((rsvd_i64)k * n + 1);
+    if (dA && dQ && dB) rsvd_b200_randqb_single_dev(dA, m, n, m, k, p, omega_seed(), dQ, m, dB, k);
+    rsvd_b200_dev_free(dA);
+    *Q = download_mat(dQ, m, k); *B = download_mat(dB, k, n);
+    rsvd_b200_dev_free(dQ); rsvd_b200_dev_free(dB);
+    rsvd_api_sync_error();
+}
+
+/* RRA:638-697: randQB_pb(M, kstep, nstep, p, 1) then the eig(B B^T) tail, ascending singular values */
+void randomized_low_rank_svd4(mat *M, idx_t kstep, idx_t nstep, idx_t p, mat **U, mat **S, mat **V) {
+    rsvd_api_begin();
+    idx_t m = M->nrows, n = M->ncols, l = max(kstep, 0) * max(nstep, 0);
+    double *dQ = NULL, *dB = NULL;
+    *U = NULL; *S = NULL; *V = NULL;
+    if (randqb_pb_device(M, kstep, nstep, p, 1, &dQ, &dB)) { *U = matrix_new(m, l); *S = matrix_new(l, l); *V = matrix_new(n, l); }
+    else {
+        double *dU = rsvd_b200_dev_alloc((rsvd_i64)m * l + 1), *dS = rsvd_b200_dev_alloc(l + 1), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * l + 1);
+        if (dU && dS && dV) rsvd_b200_svd_from_qb_asc_dev(dQ, m, m, dB, l, n, l, dU, m, dS, dV, n);
+        *U = download_mat(dU, m, l); *S = diag_from_device(dS, l); *V = download_mat(dV, n, l);
+        rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dS); rsvd_b200_dev_free(dV);
+    }
+    rsvd_b200_dev_free(dQ); rsvd_b200_dev_free(dB);
+    rsvd_api_sync_error();
+}
+
+/* shared tail of the autorank variants: SVD factors from M and an orthonormal Q (RRA:717-747) or, with q > 1, from the
+ * sketch Y through the power scheme first (RRA:858-907) */
+static void autorank_tail(mat *M, mat *Y, mat *Q, idx_t k, idx_t q, idx_t s, mat **U, mat **S, mat **V) {
+    idx_t m = M->nrows, n = M->ncols;
+    if (g_api_status || k <= 0) { *U = matrix_new(m, max(k, 0)); *S = matrix_new(max(k, 0), max(k, 0)); *V = matrix_new(n, max(k, 0)); return; }
+    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
+    double *dP = rsvd_upload(Y ? Y->d : Q->d, (size_t)m * (size_t)k);
+    double *dU = rsvd_b200_dev_alloc((rsvd_i64)m * k + 1), *dS = rsvd_b200_dev_alloc(k + 1), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * k + 1);
+    if (dA && dP && dU && dS && dV) {
+        if (Y) rsvd_b200_svd_rand_from_sketch_dev(dA, m, n, m, dP, m, k, (int)q, (int)s, dU, m, dS, dV, n);
+        else rsvd_b200_svd_from_q_dev(dA, m, n, m, dP, m, k, k, 1, dU, m, dS, dV, n);
+    }
+    rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dP);
+    *U = download_mat(dU, m, k); *S = diag_from_device(dS, k); *V = download_mat(dV, n, k);
+    rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dS); rsvd_b200_dev_free(dV);
+    rsvd_api_sync_error();
+}
+/* RRA:701-759 */
+void randomized_low_rank_svd2_autorank1(mat *M, double frac_of_max_rank, double TOL, mat **U, mat **S, mat **V) {
+    rsvd_api_begin();
+    mat *Q = NULL; idx_t k = 0;
+    estimate_rank_and_buildQ(M, frac_of_max_rank, TOL, &Q, &k);
+    autorank_tail(M, NULL, Q, k, 1, 1, U, S, V);
+    matrix_delete(Q);
+}
+/* RRA:763-822 */
+void randomized_low_rank_svd2_autorank2(mat *M, idx_t kblocksize, double TOL, mat **U, mat **S, mat **V) {
+    rsvd_api_begin();
+    mat *Y = NULL, *Q = NULL; idx_t k = 0;
+    estimate_rank_and_buildQ2(M, kblocksize, TOL, &Y, &Q, &k);
+    autorank_tail(M, NULL, Q, k, 1, 1, U, S, V);
+    matrix_delete(Y); matrix_delete(Q);
+}
+/* RRA:826-918 */
+void randomized_low_rank_svd3_autorank2(mat *M, idx_t kblocksize, double TOL, idx_t q, idx_t s, mat **U, mat **S, mat **V) {
+    rsvd_api_begin();
+    mat *Y = NULL, *Q = NULL; idx_t k = 0;
+    if (s <= 0) { rsvd_api_error("randomized_low_rank_svd3_autorank2: need s > 0"); }
+    estimate_rank_and_buildQ2(M, kblocksize, TOL, &Y, &Q, &k);
+    autorank_tail(M, Y, Q, k, q, s, U, S, V);
+    matrix_delete(Y); matrix_delete(Q);
 }

@@ -65,6 +65,14 @@ SIGNATURES = {
     "rsvd_b200_svd_from_qb_dev": (C.c_int, [dp, i64, i64, dp, i64, i64, i64, dp, i64, dp, dp, i64]),
     "rsvd_b200_id_two_sided_rand_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, dp, dp, dp, i64, dp, i64]),
     "rsvd_b200_cur_rand_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, dp, i64, dp, i64, dp, i64]),
+    "rsvd_b200_randqb_legacy_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, dp, i64, dp, i64]),
+    "rsvd_b200_randqb_single_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, u64, dp, i64, dp, i64]),
+    "rsvd_b200_svd_from_qb_asc_dev": (C.c_int, [dp, i64, i64, dp, i64, i64, i64, dp, i64, dp, dp, i64]),
+    "rsvd_b200_svd_full_dev": (C.c_int, [dp, i64, i64, i64, dp, i64, dp, dp, i64]),
+    "rsvd_b200_estimate_rank1_dev": (C.c_int, [dp, i64, i64, i64, i64, C.c_double, u64, dp, i64, C.POINTER(i64)]),
+    "rsvd_b200_estimate_rank2_dev": (C.c_int, [dp, i64, i64, i64, i64, C.c_double, u64, dp, i64, dp, i64, i64, C.POINTER(i64)]),
+    "rsvd_b200_svd_rand_from_sketch_dev": (C.c_int, [dp, i64, i64, i64, dp, i64, i64, C.c_int, C.c_int, dp, i64, dp, dp, i64]),
+    "rsvd_b200_pqr_partial_dev": (C.c_int, [dp, i64, i64, i64, i64, C.c_double, C.c_int, dp, dp, i64, dp, i64, C.POINTER(i64)]),
     "rsvd_b200_svd_percent_error_dev": (C.c_double, [dp, i64, i64, i64, dp, i64, dp, dp, i64, i64]),
     "rsvd_b200_comm_unique_id": (C.c_int, [C.c_char_p]),
     "rsvd_b200_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),

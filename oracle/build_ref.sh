@@ -21,13 +21,20 @@ if [ -d "$REF/multi_core_mkl_code" ]; then
   gcc $CF -I"$D64" "$HERE/shim/vsl_shim.c" "$D64/rank_revealing_algorithms_intel_mkl.c" \
       "$D64/matrix_vector_functions_intel_mkl.c" $LF -o "$OUT/libref64.so"
   echo "built $OUT/libref32.so $OUT/libref64.so against $OPENBLAS"
+  # The reference's drivers 2 and 4 linked with the reference itself (libref32.so): the other arm of the driver-level parity
+  # test, whose B200 arm is the relinked binary below.
+  mkdir -p "$OUT/refdrv"
+  for d in driver_multi_core_mkl2 driver_multi_core_mkl4; do
+    gcc -O2 -fopenmp -w -ffp-contract=off -I"$HERE/shim" -include "$HERE/shim/zero_malloc.h" -I"$D32" "$D32/$d.c" -L"$OUT" -lref32 \
+        -Wl,-rpath,'$ORIGIN/..' -Wl,-rpath,$PYLIBS -Wl,--disable-new-dtags -lm -o "$OUT/refdrv/$d"
+  done
   # Relink test: the reference's own drivers, UNMODIFIED, compiled against the drop-in headers (include/) and linked
   # with the B200 libraries instead of MKL.  The sources are compiled from a scratch copy (a quoted #include searches the
   # including file's directory first, where the reference's own headers live); only the binaries land in oracle/_ref/relink.
   PKG="$HERE/../lowrankmatrixdecompositioncodes_b200"
   if [ -f "$PKG/librsvd_b200_api32.so" ]; then
     mkdir -p "$OUT/relink"; TMP="$(mktemp -d)"
-    for d in driver_multi_core_mkl1 driver_multi_core_mkl3 driver_multi_core_mkl5; do
+    for d in driver_multi_core_mkl1 driver_multi_core_mkl2 driver_multi_core_mkl3 driver_multi_core_mkl4 driver_multi_core_mkl5; do
       cp "$D32/$d.c" "$TMP/$d.c"
       gcc -O2 -w -I"$HERE/../include" "$TMP/$d.c" -L"$PKG" -lrsvd_b200_api32 -lrsvd_b200 -lm -Wl,-rpath,'$ORIGIN/../../../lowrankmatrixdecompositioncodes_b200' -o "$OUT/relink/$d"
     done

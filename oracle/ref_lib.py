@@ -11,6 +11,8 @@ import ctypes as C
 import os
 import numpy as np
 
+from lowrankmatrixdecompositioncodes_b200 import _legacy_calls  # call wrappers only (no device code is touched)
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REFDIR = os.path.join(_HERE, "_ref")
 
@@ -19,7 +21,7 @@ def available(bits=32):
     return os.path.exists(os.path.join(_REFDIR, "libref%d.so" % bits))
 
 
-class RefLib:
+class RefLib(_legacy_calls.LegacyCalls):
     """One ABI flavour (32: int indices, 64: int64_t indices) of the reference library."""
 
     def __init__(self, bits=32):
@@ -66,6 +68,7 @@ class RefLib:
         L.pivotedQR_mkl.argtypes = [PM, PPM, PPM, PPV]
         L.QR_factorization_getQ.argtypes = [PM, PM]
         L.initialize_random_matrix.argtypes = [PM]
+        _legacy_calls.bind(L, I, PM, PV)
 
     # ---- marshalling -------------------------------------------------------------------------
     def set_seed(self, seed):

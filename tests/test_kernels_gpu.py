@@ -163,7 +163,7 @@ def test_jacobi_svd_and_eig(lib, n):
     assert np.linalg.norm(S @ Vn - Vn * wn) / np.linalg.norm(S) < 1e-12
 
 
-@pytest.mark.parametrize("m,n", [(12, 40), (120, 1500), (100, 2000), (300, 5000), (40, 40), (7, 3), (200, 9000)])
+@pytest.mark.parametrize("m,n", [(12, 40), (120, 1500), (100, 2000), (300, 5000), (40, 40), (7, 3), (200, 9000), (1500, 400), (2500, 2500)])
 def test_geqp3_pivots_bit_exact_vs_lapack(lib, m, n):
     from scipy.linalg import lapack
     rng = np.random.default_rng(m + n)
