@@ -118,6 +118,13 @@ int rsvd_b200_id_two_sided_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsv
 /* cur_rand_decomp_fixed_rank (RRA:2191-2258). C m x k, U k x k, R k x n. */
 int rsvd_b200_cur_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q, int s,
                            uint64_t seed, double *C, rsvd_i64 ldc, double *U, rsvd_i64 ldu, double *R, rsvd_i64 ldr);
+/* ---- binary matrix files <-> device memory ----
+ * The reference's format (MVF:77-133; 64-bit MVF64:78-135): two int32 (index_bits = 32) or int64 (64) m, n, then ROW-major
+ * doubles.  Row blocks are DMA'd as they lie in the file and transposed on the device; the host never holds the matrix.
+ * load: *dA is allocated by the library (free with rsvd_b200_dev_free), column-major m x n with ld m. */
+int rsvd_b200_load_binary_dev(const char *path, int index_bits, double **dA, rsvd_i64 *m, rsvd_i64 *n);
+int rsvd_b200_store_binary_dev(const char *path, int index_bits, const double *dA, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n);
+
 /* ---- deterministic baselines and legacy entry points ---- */
 /* randQB_pb (RRA:1425-1572): as randqb_dev in rank mode but re-orthogonalising against all previous blocks on EVERY step
  * (RRA:1503-1528); p = power steps (loop j <= p), no tolerance.  Q m x kstep*nstep, B kstep*nstep x n. */

@@ -3,6 +3,7 @@
 // cuBLAS build re-uploads both operands on EVERY GEMM call, matrix_vector_functions_mkl_and_cublas.c:566-577);
 // here one upload per API call keeps A resident for all 2q passes.
 #include "common.cuh"
+#include <algorithm>
 #include <stdarg.h>
 #include <mutex>
 
@@ -228,7 +229,93 @@ rsvd_i64 rsvd_b200_get_option(const char *name) {
 
 double *rsvd_b200_dev_alloc(rsvd_i64 n) { return dalloc((size_t)n); }
 void rsvd_b200_dev_free(double *d) { dfree(d); }
+// ---- binary matrix files <-> device ------------------------------------------------------------
+// The reference's file format (matrix_load_from_binary_file / matrix_write_to_binary_file, MVF:77-133, MVF64:78-135) is a
+// header of two int32 (or int64) followed by ROW-major doubles.  A block of rows is a column-major (n x rows) matrix, so it
+// is DMA'd as it lies in the file and transposed into the column-major device matrix by a kernel: the host never transposes
+// and never holds the matrix.  File reads of block i+1 overlap the DMA + transpose of block i (two pinned staging buffers).
+static int load_binary_dev(const char *path, int index_bits, double **dA_out, i64 *m_out, i64 *n_out) {
+    ensure_init();
+    Ctx &c = ctx();
+    if (!c.inited) return 1;
+    *dA_out = nullptr; *m_out = 0; *n_out = 0;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) { set_error("rsvd_b200: cannot open %s", path); return 1; }
+    i64 m = -1, n = -1;
+    if (index_bits == 64) { long long h[2]; if (fread(h, 8, 2, fp) == 2) { m = h[0]; n = h[1]; } }
+    else { int h[2]; if (fread(h, 4, 2, fp) == 2) { m = h[0]; n = h[1]; } }
+    if (m < 0 || n < 0) { set_error("rsvd_b200: bad header in %s", path); fclose(fp); return 1; }
+    const size_t row_bytes = (size_t)n * 8;
+    if (row_bytes > Staging::CHUNK) { set_error("rsvd_b200: rows of %s exceed the %zu-byte staging buffer", path, Staging::CHUNK); fclose(fp); return 1; }
+    g_staging.init();
+    const i64 rb = row_bytes ? (i64)(Staging::CHUNK / row_bytes) : 1;
+    double *A = dalloc((size_t)m * n + 1);
+    double *ds[2] = {dalloc((size_t)rb * n + 1), dalloc((size_t)rb * n + 1)};
+    bool used[2] = {false, false};
+    int b = 0;
+    for (i64 i0 = 0; i0 < m && !g_status; i0 += rb, b ^= 1) {
+        const i64 rows = std::min(rb, m - i0);
+        if (used[b]) RSVD_CUDA(cudaEventSynchronize(g_staging.ev[b]));
+        if (fread(g_staging.buf[b], 8, (size_t)rows * n, fp) != (size_t)rows * n) { set_error("rsvd_b200: %s is truncated", path); break; }
+        RSVD_CUDA(cudaMemcpyAsync(ds[b], g_staging.buf[b], (size_t)rows * row_bytes, cudaMemcpyHostToDevice, c.stream));
+        RSVD_CUDA(cudaEventRecord(g_staging.ev[b], c.stream));
+        used[b] = true;
+        transpose(ds[b], n, A + i0, m, n, rows);          // (n x rows, ld n)^T -> rows i0.. of A (ld m)
+    }
+    fclose(fp);
+    RSVD_CUDA(cudaStreamSynchronize(c.stream));
+    dfree(ds[0]); dfree(ds[1]);
+    if (g_status) { dfree(A); return 1; }
+    *dA_out = A; *m_out = m; *n_out = n;
+    return 0;
+}
+
+static int store_binary_dev(const char *path, int index_bits, const double *A, i64 lda, i64 m, i64 n) {
+    ensure_init();
+    Ctx &c = ctx();
+    if (!c.inited) return 1;
+    const size_t row_bytes = (size_t)n * 8;
+    if (row_bytes > Staging::CHUNK) { set_error("rsvd_b200: rows of %lld doubles exceed the staging buffer", (long long)n); return 1; }
+    FILE *fp = fopen(path, "wb");
+    if (!fp) { set_error("rsvd_b200: cannot open %s for writing", path); return 1; }
+    if (index_bits == 64) { long long h[2] = {m, n}; fwrite(h, 8, 2, fp); }
+    else { int h[2] = {(int)m, (int)n}; fwrite(h, 4, 2, fp); }
+    g_staging.init();
+    const i64 rb = row_bytes ? (i64)(Staging::CHUNK / row_bytes) : 1;
+    double *ds[2] = {dalloc((size_t)rb * n + 1), dalloc((size_t)rb * n + 1)};
+    i64 pend_rows[2] = {0, 0};
+    bool used[2] = {false, false};
+    int b = 0;
+    for (i64 i0 = 0; (i0 < m || used[0] || used[1]) && !g_status; i0 += rb, b ^= 1) {
+        if (used[b]) {                                      // block issued two iterations ago has landed: write it out
+            RSVD_CUDA(cudaEventSynchronize(g_staging.ev[b]));
+            if (fwrite(g_staging.buf[b], 8, (size_t)pend_rows[b] * n, fp) != (size_t)pend_rows[b] * n) { set_error("rsvd_b200: short write to %s", path); break; }
+            used[b] = false;
+        }
+        if (i0 < m) {
+            const i64 rows = std::min(rb, m - i0);
+            transpose(A + i0, lda, ds[b], n, rows, n);      // rows i0.. (rows x n, ld lda)^T -> (n x rows, ld n) = row-major block
+            RSVD_CUDA(cudaMemcpyAsync(g_staging.buf[b], ds[b], (size_t)rows * row_bytes, cudaMemcpyDeviceToHost, c.stream));
+            RSVD_CUDA(cudaEventRecord(g_staging.ev[b], c.stream));
+            pend_rows[b] = rows; used[b] = true;
+        }
+    }
+    fclose(fp);
+    RSVD_CUDA(cudaStreamSynchronize(c.stream));
+    dfree(ds[0]); dfree(ds[1]);
+    return g_status;
+}
+
 int rsvd_b200_h2d(double *d, const double *h, rsvd_i64 n) { return copy_h2d(d, h, (size_t)n); }
+int rsvd_b200_load_binary_dev(const char *path, int index_bits, double **dA, rsvd_i64 *m, rsvd_i64 *n) {
+    i64 mm = 0, nn = 0;
+    int rc = load_binary_dev(path, index_bits, dA, &mm, &nn);
+    *m = mm; *n = nn;
+    return rc;
+}
+int rsvd_b200_store_binary_dev(const char *path, int index_bits, const double *dA, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n) {
+    return store_binary_dev(path, index_bits, dA, lda, m, n);
+}
 int rsvd_b200_d2h(double *h, const double *d, rsvd_i64 n) { return copy_d2h(h, d, (size_t)n); }
 
 void *rsvd_b200_host_alloc(size_t bytes) {

@@ -99,7 +99,11 @@ mat *matrix_load_from_binary_file(char *fname) {
         return NULL;
     }
     mat *M = matrix_new(m, n);
-    const size_t RB = 64;   /* rows per block */
+    /* blocks of up to 32 MB of whole rows; each block is scattered into the column-major matrix by all cores, one cache line
+     * of the row-major block (8 columns of one row) at a time */
+    size_t RB = n ? (((size_t)32 << 20) / ((size_t)n * sizeof(double))) : 1;
+    if (RB < 8) RB = 8;
+    if (RB > (size_t)(m ? m : 1)) RB = (size_t)(m ? m : 1);
     double *buf = (double *)malloc(RB * (size_t)(n ? n : 1) * sizeof(double));
     for (size_t i0 = 0; i0 < (size_t)m; i0 += RB) {
         size_t rb = (size_t)m - i0 < RB ? (size_t)m - i0 : RB;
@@ -107,8 +111,12 @@ mat *matrix_load_from_binary_file(char *fname) {
             rsvd_api_error("matrix_load_from_binary_file: %s is truncated", fname);
             break;
         }
-        for (size_t j = 0; j < (size_t)n; ++j)
-            for (size_t r = 0; r < rb; ++r) M->d[j * (size_t)m + i0 + r] = buf[r * (size_t)n + j];
+        #pragma omp parallel for schedule(static)
+        for (long long j0 = 0; j0 < (long long)n; j0 += 8) {
+            size_t j1 = (size_t)j0 + 8 < (size_t)n ? (size_t)j0 + 8 : (size_t)n;
+            for (size_t r = 0; r < rb; ++r)
+                for (size_t j = (size_t)j0; j < j1; ++j) M->d[j * (size_t)m + i0 + r] = buf[r * (size_t)n + j];
+        }
     }
     free(buf);
     fclose(fp);
@@ -121,12 +129,18 @@ void matrix_write_to_binary_file(mat *M, char *fname) {
     idx_t m = M->nrows, n = M->ncols;
     fwrite(&m, sizeof(idx_t), 1, fp);
     fwrite(&n, sizeof(idx_t), 1, fp);
-    const size_t RB = 64;
+    size_t RB = n ? (((size_t)32 << 20) / ((size_t)n * sizeof(double))) : 1;
+    if (RB < 8) RB = 8;
+    if (RB > (size_t)(m ? m : 1)) RB = (size_t)(m ? m : 1);
     double *buf = (double *)malloc(RB * (size_t)(n ? n : 1) * sizeof(double));
     for (size_t i0 = 0; i0 < (size_t)m; i0 += RB) {
         size_t rb = (size_t)m - i0 < RB ? (size_t)m - i0 : RB;
-        for (size_t j = 0; j < (size_t)n; ++j)
-            for (size_t r = 0; r < rb; ++r) buf[r * (size_t)n + j] = M->d[j * (size_t)m + i0 + r];
+        #pragma omp parallel for schedule(static)
+        for (long long j0 = 0; j0 < (long long)n; j0 += 8) {
+            size_t j1 = (size_t)j0 + 8 < (size_t)n ? (size_t)j0 + 8 : (size_t)n;
+            for (size_t r = 0; r < rb; ++r)
+                for (size_t j = (size_t)j0; j < j1; ++j) buf[r * (size_t)n + j] = M->d[j * (size_t)m + i0 + r];
+        }
         fwrite(buf, sizeof(double), rb * (size_t)n, fp);
     }
     free(buf);

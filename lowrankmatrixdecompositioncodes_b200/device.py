@@ -49,3 +49,38 @@ def svd_rand(A_cm, k, p, vnum=1, q=2, s=1, seed=777, omega=None):
                                              ptr(omega) if omega is not None else None, ptr(U), m, ptr(S), ptr(V), n)
     native.check(rc)
     return U, S, V
+
+
+class DeviceMatrix:
+    """A column-major m x n matrix in library-owned device memory (rsvd_b200_load_binary_dev).  `free()` releases it."""
+
+    def __init__(self, ptr_, m, n):
+        self.ptr, self.m, self.n = ptr_, m, n
+
+    def free(self):
+        if self.ptr:
+            native.dev().rsvd_b200_dev_free(self.ptr)
+            self.ptr = None
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.n, self.m), "typestr": "<f8", "data": (self.ptr, False), "version": 2}
+
+    def to_torch(self):
+        """an owned (n, m) torch tensor (column-major convention of this module) with the same contents"""
+        native.dev().rsvd_b200_sync()
+        if self.m * self.n == 0:
+            return new_cm(self.m, self.n)
+        return torch.as_tensor(self, device="cuda").clone()
+
+
+def load_binary(path, index_bits=32):
+    """Reference-format binary matrix file -> device memory, no host copy of the matrix (include/rsvd_b200.h)."""
+    p, m, n = C.c_void_p(), C.c_longlong(), C.c_longlong()
+    rc = native.dev().rsvd_b200_load_binary_dev(path.encode(), index_bits, C.byref(p), C.byref(m), C.byref(n))
+    native.check(rc)
+    return DeviceMatrix(p.value, m.value, n.value)
+
+
+def store_binary(path, A_ptr, lda, m, n, index_bits=32):
+    native.check(native.dev().rsvd_b200_store_binary_dev(path.encode(), index_bits, A_ptr, lda, m, n))
