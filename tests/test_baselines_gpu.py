@@ -264,3 +264,22 @@ def test_relinked_drivers_2_and_4_match_the_reference_output(tmp_path, which):
     assert ranks[:len(granks)] == granks
     for e, g in zip(errs, gerrs):
         assert e == pytest.approx(g, rel=2e-5, abs=2e-6)
+
+
+def test_baselines_through_the_int64_abi(api):
+    """multi_core_mkl_code_64bit: the same entry points with int64_t indices (rank_revealing_algorithms_intel_mkl.h:3-91 there)."""
+    if not ref_lib.available(64):
+        pytest.skip("compiled 64-bit reference not present")
+    api64, ref64 = pkg.Api(64), ref_lib.RefLib(64)
+    A = decaying(180, 240, 70, seed=64)
+    f, Q, R, I = api64.pqr(A, 25, 0.0)
+    f0, Q0, R0, I0 = ref64.pqr(A, 25, 0.0)
+    assert f == f0 == 25 and np.array_equal(I, I0) and relerr(R, R0) < 1e-9 and relerr(Q, Q0) < 1e-9
+    f, Ic, Ir, T, S = api64.id_two_sided_decomp(A, 0, 1e-5)
+    f0, Ic0, Ir0, T0, S0 = ref64.id_two_sided_decomp(A, 0, 1e-5)
+    assert f == f0 and np.array_equal(Ic, Ic0) and np.array_equal(Ir, Ir0) and relerr(T, T0) < 1e-8 and relerr(S, S0) < 1e-8
+    Qb, Bb = api64.randQB_pb(A, 8, 3, 1, 1, seed=5)
+    Q0, B0 = ref64.randQB_pb(A, 8, 3, 1, 1, seed=5)
+    assert relerr(Qb @ Bb, Q0 @ B0) < 1e-9
+    fr, U, S_, V = api64.svd_decomp(A, 20, 0.0)
+    assert fr == 20 and np.max(np.abs(np.diag(S_) - np.linalg.svd(A, compute_uv=False)[:20])) < 1e-13
