@@ -106,71 +106,194 @@ __device__ __forceinline__ bool grid_barrier(int *bar, int gen, int *err) {
     return ok_s != 0;
 }
 
+// ---- pair schedule shared by the persistent kernel and the replay kernel --------------------------------------------------
+// Columns are grouped in blocks of BW; the NBk blocks (NBk even) play a round-robin tournament, CTA i holding the two blocks
+// that meet in the current round.  A sweep of N - 1 = NBk*BW - 1 steps, each of N/2 disjoint pairs, is
+//   steps 0 .. BW-2            : the pairs INSIDE every block (round-robin among its BW columns; CTA i serves its round-0 blocks)
+//   then, per tournament round : BW steps pairing column j of block P with column (j + t) mod BW of block Q, t = 0..BW-1,
+// so a CTA rotates 2*BW register-resident columns BW times between two device-wide barriers instead of once.
+// BW = 1 is the plain round-robin of column pairs.  Pair slot of (CTA i, pair j) = i*BW + j.
+__device__ __forceinline__ void block_pair(int NBk, int rb, int i, int &P, int &Q) {
+    const int M = NBk - 1;
+    if (i == 0) { P = M; Q = rb; }
+    else { P = (rb + i) % M; Q = (rb - i + M) % M; }
+}
+// local (register) column indices of pair j at intra-block step t: 0..BW-1 = block P, BW..2BW-1 = block Q
+template <int BW>
+__device__ __forceinline__ void intra_pair(int t, int j, int &ca, int &cb) {
+    const int off = (j < BW / 2) ? 0 : BW, jj = (j < BW / 2) ? j : j - BW / 2;
+    int x, y;
+    if (jj == 0) { x = BW - 1; y = t; }
+    else { x = (t + jj) % (BW - 1); y = (t - jj + (BW - 1)) % (BW - 1); }
+    ca = off + x; cb = off + y;
+}
+// global column indices (p, q) of pair slot (i, j) at sweep-local step st
+template <int BW>
+__device__ __forceinline__ void pair_at(int NBk, int st, int i, int j, int &p, int &q) {
+    int P, Q;
+    if (BW > 1 && st < BW - 1) {
+        block_pair(NBk, 0, i, P, Q);
+        int ca, cb;
+        intra_pair<(BW > 1 ? BW : 2)>(st, j, ca, cb);
+        p = (ca < BW ? P * BW + ca : Q * BW + ca - BW);
+        q = (cb < BW ? P * BW + cb : Q * BW + cb - BW);
+    } else {
+        const int u = st - (BW - 1), rb = u / BW, t = u % BW;
+        block_pair(NBk, rb, i, P, Q);
+        p = P * BW + j;
+        q = Q * BW + (j + t) % BW;
+    }
+}
+
+// ---- rotation parameters on the critical path ------------------------------------------------------------------------------
+// IEEE double sqrt/div are ~12-instruction dependent chains each and the textbook formulas need five of them per rotation
+// (plus two more for the convergence test).  Here: MUFU seeds (rsqrt/rcp.approx.f64, ~20 bits, full double range) refined by
+// a third-order step where full precision matters (cs: the rotation must be orthogonal to machine precision) and a
+// second-order step where it does not (t: an error of 1e-12 relative only leaves a cosine 1e-12 times the one annihilated).
+__device__ __forceinline__ double rsqrt_seed(double x) { double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
+__device__ __forceinline__ double rcp_seed(double x) { double y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
+__device__ __forceinline__ double rsqrt_full(double x) {      // 1/sqrt(x) to ~1 ulp for normal x
+    const double y0 = rsqrt_seed(x);
+    const double e = fma(-x * y0, y0, 1.0);
+    return fma(y0, e * fma(0.375, e, 0.5), y0);
+}
+// rotation annihilating c = x.y given a = x.x, b = y.y:  x' = cs x - sn y,  y' = sn x + cs y;  t = sn/cs
+__device__ __forceinline__ void rot_params(double a, double b, double c, double &cs, double &sn, double &t) {
+    const double d = b - a, c2 = 2.0 * c;
+    const double s = fma(d, d, c2 * c2);
+    if (!(s > 1e-290 && s < 1e290)) {                         // out of the seeds' comfortable range: textbook formulas
+        const double zeta = d / c2;
+        t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        cs = 1.0 / sqrt(1.0 + t * t); sn = cs * t;
+        return;
+    }
+    const double h = s * rsqrt_full(s);                       // sqrt(d^2 + (2c)^2)
+    const double den = fabs(d) + h;
+    double r = rcp_seed(den);
+    r = r * fma(-den, r, 2.0);
+    r = r * fma(-den, r, 2.0);
+    t = copysign(c2, c2 * d) * r;                             // = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = d / 2c
+    if (d == 0.0) t = copysign(1.0, c2);
+    cs = rsqrt_full(fma(t, t, 1.0));
+    sn = cs * t;
+}
+
+template <int K>
+__device__ __forceinline__ void block_sumK(double (&v)[K], double *sh) {   // sh: K * (JT/32) doubles, one __syncthreads
+#pragma unroll
+    for (int e = 0; e < K; ++e)
+        for (int o = 16; o > 0; o >>= 1) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+#pragma unroll
+        for (int e = 0; e < K; ++e) sh[e * (JT / 32) + w] = v[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < K; ++e) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < JT / 32; ++i) t += sh[e * (JT / 32) + i];
+        v[e] = t;
+    }
+}
+
 // ctl[0] = barrier counter, ctl[1] = error flag, ctl[2] = sweeps done, ctl[8 + s] = CTAs that rotated in sweep s,
 // (unsigned long long *)(ctl + 4)[0] = bit pattern of the largest |cosine| met in the current sweep (positive doubles order like integers)
-__global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ldg, double *V, i64 ldv, int n, int N, double tol,
-                                                               int max_sweeps, int *ctl, double2 *rotlog) {
-    __shared__ double sh[3 * (JT / 32)];
+// The rotations are only LOGGED (rotlog[step][slot] = (c, s), identity when nothing was rotated): V is rebuilt afterwards by
+// jacobi_replay_kernel, off the critical path.  RPT = rows per thread (JT*RPT >= n).
+template <int BW, int RPT>
+__global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ldg, int n, int NBk, double tol, int max_sweeps, int *ctl,
+                                                               double2 *rotlog) {
+    __shared__ double sh[2][3 * BW * (JT / 32) > 2 * BW * (JT / 32) ? 3 * BW * (JT / 32) : 2 * BW * (JT / 32)];
     const int i = blockIdx.x;
-    int gen = 0;
+    const int N = NBk * BW, half = N / 2;
+    int gen = 0, shb = 0;
     unsigned long long *maxcos = reinterpret_cast<unsigned long long *>(ctl + 4);
-    int gs = 0;      // global step index
+    i64 gs = 0;      // global step index
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
         int rotated = 0;
         double cmax = 0.0;
-        for (int r = 0; r < N - 1; ++r, ++gs) {
-            double2 applied = make_double2(1.0, 0.0);
-            int p, q;
-            if (i == 0) { p = N - 1; q = r; }
-            else { p = (r + i) % (N - 1); q = (r - i + (N - 1)) % (N - 1); }
-            if (p > q) { int t = p; p = q; q = t; }
-            if (q < n) {
-                double *gp = G + (i64)p * ldg, *gq = G + (i64)q * ldg;
-                double xp[JR], xq[JR];
-                double a = 0.0, b = 0.0, c = 0.0;
+        for (int rb = 0; rb < NBk - 1; ++rb) {
+            int P, Q;
+            block_pair(NBk, rb, i, P, Q);
+            // ---- load the 2*BW columns and their squared norms
+            double X[2 * BW][RPT], nrm[2 * BW];
+            int col[2 * BW];
 #pragma unroll
-                for (int k = 0; k < JR; ++k) {
-                    int row = threadIdx.x + k * JT;
-                    xp[k] = row < n ? __ldcg(gp + row) : 0.0;     // L2 loads: other SMs wrote these columns in the previous step
-                    xq[k] = row < n ? __ldcg(gq + row) : 0.0;
-                    a = fma(xp[k], xp[k], a);
-                    b = fma(xq[k], xq[k], b);
-                    c = fma(xp[k], xq[k], c);
+            for (int cc = 0; cc < 2 * BW; ++cc) {
+                col[cc] = (cc < BW) ? P * BW + cc : Q * BW + cc - BW;
+                const double *g = G + (i64)col[cc] * ldg;
+                double a = 0.0;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    const int row = threadIdx.x + k * JT;
+                    X[cc][k] = (row < n && col[cc] < n) ? __ldcg(g + row) : 0.0;   // L2 loads: other SMs wrote these columns in the previous round
+                    a = fma(X[cc][k], X[cc][k], a);
                 }
-                __syncthreads();     // sh reuse across steps
-                block_sum3(a, b, c, sh);
-                if (fabs(c) > tol * sqrt(a * b) && a != 0.0 && b != 0.0) {
-                    const double zeta = (b - a) / (2.0 * c);
-                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-                    rotated = 1;
-                    cmax = fmax(cmax, fabs(c) / sqrt(a * b));
+                nrm[cc] = a;
+            }
+            block_sumK<2 * BW>(nrm, sh[shb]); shb ^= 1;
+            bool dirty[2 * BW];
 #pragma unroll
-                    for (int k = 0; k < JR; ++k) {
-                        int row = threadIdx.x + k * JT;
-                        if (row < n) {
-                            gp[row] = cs * xp[k] - sn * xq[k];
-                            gq[row] = sn * xp[k] + cs * xq[k];
+            for (int cc = 0; cc < 2 * BW; ++cc) dirty[cc] = false;
+            // ---- the steps of this round: intra-block pairs first (round 0 only), then the BW cross steps
+            const int nintra = (BW > 1 && rb == 0) ? BW - 1 : 0;
+#pragma unroll
+            for (int stp = 0; stp < (BW > 1 ? BW - 1 : 0) + BW; ++stp) {
+                const bool intra = stp < (BW > 1 ? BW - 1 : 0);
+                if (intra && nintra == 0) continue;
+                int ca[BW], cb[BW];
+                double dots[BW];
+#pragma unroll
+                for (int j = 0; j < BW; ++j) {
+                    if (intra) intra_pair<(BW > 1 ? BW : 2)>(stp, j, ca[j], cb[j]);
+                    else { ca[j] = j; cb[j] = BW + (j + (stp - (BW > 1 ? BW - 1 : 0))) % BW; }
+                    double c = 0.0;
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k) c = fma(X[ca[j]][k], X[cb[j]][k], c);
+                    dots[j] = c;
+                }
+                block_sumK<BW>(dots, sh[shb]); shb ^= 1;
+#pragma unroll
+                for (int j = 0; j < BW; ++j) {
+                    const double a = nrm[ca[j]], b = nrm[cb[j]], c = dots[j];
+                    double2 applied = make_double2(1.0, 0.0);
+                    const double ab = a * b;
+                    const bool inrange = ab > 1e-280 && ab < 1e280;             // else c*c or a*b may under/overflow
+                    if ((inrange ? c * c > tol * tol * ab : fabs(c) > tol * sqrt(a) * sqrt(b)) && a != 0.0 && b != 0.0) {
+                        double cs, sn, t;
+                        rot_params(a, b, c, cs, sn, t);
+                        rotated = 1;
+                        cmax = fmax(cmax, inrange ? c * c * rcp_seed(ab) : (c / a) * (c / b));   // cosine^2 (20 bits suffice: compared with 1e-16)
+#pragma unroll
+                        for (int k = 0; k < RPT; ++k) {
+                            const double x = X[ca[j]][k], y = X[cb[j]][k];
+                            X[ca[j]][k] = cs * x - sn * y;
+                            X[cb[j]][k] = sn * x + cs * y;
                         }
+                        nrm[ca[j]] = fmax(a - t * c, 0.0);      // norms after the rotation that annihilates c
+                        nrm[cb[j]] = b + t * c;
+                        dirty[ca[j]] = true; dirty[cb[j]] = true;
+                        applied = make_double2(cs, sn);
                     }
-                    applied = make_double2(cs, sn);
-                    if (!rotlog) {   // no log: rotate the columns of V in place
-                        double *vp = V + (i64)p * ldv, *vq = V + (i64)q * ldv;
+                    if (threadIdx.x == 0) rotlog[gs * half + i * BW + j] = applied;
+                }
+                ++gs;
+            }
+            // ---- write the rotated columns back
 #pragma unroll
-                        for (int k = 0; k < JR; ++k) {
-                            int row = threadIdx.x + k * JT;
-                            if (row < n) {
-                                double y = __ldcg(vp + row), z = __ldcg(vq + row);
-                                vp[row] = cs * y - sn * z;
-                                vq[row] = sn * y + cs * z;
-                            }
-                        }
+            for (int cc = 0; cc < 2 * BW; ++cc) {
+                if (dirty[cc]) {
+                    double *g = G + (i64)col[cc] * ldg;
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k) {
+                        const int row = threadIdx.x + k * JT;
+                        if (row < n) g[row] = X[cc][k];
                     }
                 }
             }
-            // the V update is off the critical path: the rotation is logged and replayed on V afterwards (jacobi_replay_kernel)
-            if (rotlog && threadIdx.x == 0) rotlog[(i64)gs * (N / 2) + i] = applied;
-            if (r == N - 2 && rotated && threadIdx.x == 0) {
+            if (rb == NBk - 2 && rotated && threadIdx.x == 0) {
                 atomicAdd(ctl + 8 + sweep, 1);
                 atomicMax(maxcos + (sweep & 1), (unsigned long long)__double_as_longlong(cmax));
             }
@@ -179,52 +302,49 @@ __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ld
         const int nrot = *((volatile int *)(ctl + 8 + sweep));
         const double swept = __longlong_as_double((long long)*((volatile unsigned long long *)(maxcos + (sweep & 1))));
         if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[2] = sweep + 1; maxcos[(sweep + 1) & 1] = 0ull; }
-        // Converged when nothing was rotated, or when every cosine met in this sweep was already <= 1e-8: Jacobi converges
-        // quadratically, so the rotations just applied leave cosines of order 1e-16 and the confirming sweep is skipped.
-        if (nrot == 0 || swept <= 1.0e-8) break;
+        // Converged when nothing was rotated, or when every cosine met in this sweep was already <= 1e-8 (swept holds the
+        // largest SQUARED cosine): Jacobi converges quadratically, so the rotations just applied leave cosines of order 1e-16
+        // and the confirming sweep is skipped.
+        if (nrot == 0 || swept <= 1.0e-16) break;
     }
 }
 
 // Replays the logged rotations on V = I.  Rows of V are independent, so one CTA owns RR rows (all N columns, in shared
-// memory) and one thread owns pair slot i: a step is one rotation of RR-row column pieces per thread and one __syncthreads,
+// memory) and one thread owns a pair slot: a step is one rotation of RR-row column pieces per thread and one __syncthreads,
 // with the log entries of the next RPB steps prefetched while the current RPB are applied.  The whole accumulated product
 // costs about a millisecond instead of one dependent L2 round trip per Jacobi step (measured: 1.6 of the 4.6 us of a step).
 constexpr int RPB = 8;
-template <int RR>
-__global__ void __launch_bounds__(RR == 4 ? 608 : 1024) jacobi_replay_kernel(double *V, i64 ldv, int n, int N, int total_steps,
-                                                             const double2 *__restrict__ rotlog) {
+template <int RR, int BW>
+__global__ void __launch_bounds__(RR == 4 ? 608 : 1024) jacobi_replay_kernel(double *V, i64 ldv, int n, int NBk, i64 total_steps,
+                                                                             const double2 *__restrict__ rotlog) {
     extern __shared__ __align__(16) double T[];          // [N][RR]
+    const int N = NBk * BW, half = N / 2;
     const int r0 = blockIdx.x * RR;
     for (int e = threadIdx.x; e < N * RR; e += blockDim.x) {
         const int col = e / RR, rr = e % RR;
         T[e] = (col == r0 + rr) ? 1.0 : 0.0;
     }
     __syncthreads();
-    const int half = N / 2;
-    const int i = threadIdx.x;
-    const bool active = i < half;
+    const int slot = threadIdx.x;
+    const bool active = slot < half;
+    const int ci = slot / BW, cj = slot % BW;
     const double2 ident = make_double2(1.0, 0.0);
     double2 cur[RPB], nxt[RPB];
 #pragma unroll
-    for (int b = 0; b < RPB; ++b) cur[b] = (active && b < total_steps) ? __ldg(rotlog + (i64)b * half + i) : ident;
-    int r = 0;
-    for (int base = 0; base < total_steps; base += RPB) {
+    for (int b = 0; b < RPB; ++b) cur[b] = (active && b < total_steps) ? __ldg(rotlog + (i64)b * half + slot) : ident;
+    int st = 0;      // sweep-local step
+    for (i64 base = 0; base < total_steps; base += RPB) {
 #pragma unroll
         for (int b = 0; b < RPB; ++b) {
-            const int g = base + RPB + b;
-            nxt[b] = (active && g < total_steps) ? __ldg(rotlog + (i64)g * half + i) : ident;
+            const i64 g = base + RPB + b;
+            nxt[b] = (active && g < total_steps) ? __ldg(rotlog + g * half + slot) : ident;
         }
 #pragma unroll
         for (int b = 0; b < RPB; ++b) {
             if (base + b < total_steps) {     // uniform
                 if (cur[b].y != 0.0) {        // identity entries (nothing rotated, padded column, inactive thread) are skipped
                     int p, q;
-                    if (i == 0) { p = N - 1; q = r; }
-                    else {
-                        p = r + i; if (p >= N - 1) p -= N - 1;
-                        q = r - i; if (q < 0) q += N - 1;
-                    }
-                    if (p > q) { int t = p; p = q; q = t; }
+                    pair_at<BW>(NBk, st, ci, cj, p, q);
                     double2 *tp = reinterpret_cast<double2 *>(T + p * RR), *tq = reinterpret_cast<double2 *>(T + q * RR);
                     const double cs = cur[b].x, sn = cur[b].y;
 #pragma unroll
@@ -234,7 +354,7 @@ __global__ void __launch_bounds__(RR == 4 ? 608 : 1024) jacobi_replay_kernel(dou
                         tq[h] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
                     }
                 }
-                if (++r == N - 1) r = 0;
+                if (++st == N - 1) st = 0;
                 __syncthreads();
             }
         }
@@ -247,11 +367,52 @@ __global__ void __launch_bounds__(RR == 4 ? 608 : 1024) jacobi_replay_kernel(dou
     }
 }
 
-template <int RR>
-static void launch_replay(double *V, i64 ldv, int n, int N, int steps, const double2 *rotlog, cudaStream_t st) {
+template <int RR, int BW>
+static void launch_replay(double *V, i64 ldv, int n, int NBk, i64 steps, const double2 *rotlog, cudaStream_t st) {
+    const int N = NBk * BW;
     const size_t smem = (size_t)N * RR * sizeof(double);
-    RSVD_CUDA(cudaFuncSetAttribute(jacobi_replay_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    jacobi_replay_kernel<RR><<<(n + RR - 1) / RR, (N / 2 + 31) / 32 * 32, smem, st>>>(V, ldv, n, N, steps, rotlog);
+    RSVD_CUDA(cudaFuncSetAttribute(jacobi_replay_kernel<RR, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jacobi_replay_kernel<RR, BW><<<(n + RR - 1) / RR, (N / 2 + 31) / 32 * 32, smem, st>>>(V, ldv, n, NBk, steps, rotlog);
+}
+
+// one (BW, RPT) instantiation of the persistent path; returns sweeps, -1 on a barrier time-out, -2 when it could not launch
+template <int BW, int RPT>
+static int run_persistent(double *G, i64 ldg, double *V, i64 ldv, int n, double tol, int max_sweeps) {
+    Ctx &c = ctx();
+    static int blocks_per_sm = -1;
+    if (blocks_per_sm < 0) RSVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_persistent_kernel<BW, RPT>, JT, 0));
+    int NBk = 2 * ((n + 2 * BW - 1) / (2 * BW));
+    const int N = NBk * BW, half = N / 2;
+    if (NBk / 2 > blocks_per_sm * c.sms || half > 1024) return -2;
+    const size_t log_entries = (size_t)max_sweeps * (N - 1) * half;
+    if (log_entries * sizeof(double2) > ((size_t)1 << 30)) return -2;
+    int *ctl = (int *)dalloc_bytes(64 * sizeof(int));
+    double2 *rotlog = (double2 *)dalloc_bytes(log_entries * sizeof(double2));
+    if (g_status) return -2;
+    RSVD_CUDA(cudaMemsetAsync(ctl, 0, 64 * sizeof(int), c.stream));
+    int ms = max_sweeps;
+    void *args[] = {&G, &ldg, (void *)&n, &NBk, (void *)&tol, &ms, &ctl, &rotlog};
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)jacobi_persistent_kernel<BW, RPT>, dim3(NBk / 2), dim3(JT), args, 0, c.stream);
+    int sweeps = -2;
+    if (e == cudaSuccess) {
+        count_launch();
+        RSVD_CUDA(cudaMemcpyAsync(c.h_flag + 16, ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        RSVD_CUDA(cudaStreamSynchronize(c.stream));
+        if (c.h_flag[17]) { set_error("rsvd_b200: Jacobi device-wide barrier timed out"); sweeps = -1; }
+        else {
+            sweeps = c.h_flag[18];
+            const i64 steps = (i64)sweeps * (N - 1);
+            if (n <= 1184) launch_replay<4, BW>(V, ldv, n, NBk, steps, rotlog, c.stream);   // <= 2 CTAs per SM, one wave
+            else launch_replay<8, BW>(V, ldv, n, NBk, steps, rotlog, c.stream);
+            count_launch();
+            if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d (persistent, %d columns per CTA)\n", n, sweeps, 2 * BW);
+        }
+    } else {
+        (void)cudaGetLastError();
+    }
+    dfree(ctl);
+    dfree(rotlog);
+    return sweeps;
 }
 
 // sigma[j] = ||G(:,j)||, one warp per column
@@ -291,43 +452,19 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
     const int max_sweeps = 40;
     int sweeps = 0;
 
-    // persistent path: all N/2 CTAs co-resident (cooperative launch guarantees it or fails cleanly)
-    static int coop = -1, blocks_per_sm = 0;
-    if (coop < 0) {
-        RSVD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
-        RSVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_persistent_kernel, JT, 0));
-    }
-    if (coop > 0 && N / 2 <= blocks_per_sm * c.sms && !getenv("RSVD_B200_JACOBI_GRAPH")) {
-        int *ctl = (int *)dalloc_bytes(64 * sizeof(int));
-        RSVD_CUDA(cudaMemsetAsync(ctl, 0, 64 * sizeof(int), c.stream));
-        int ms = max_sweeps;
-        // rotation log for the deferred V update (identity entries where nothing was rotated); falls back to in-place V
-        // updates when the log would not fit the replay kernel's shared memory or 1 GiB
-        const size_t log_entries = (size_t)max_sweeps * (N - 1) * (N / 2);
-        double2 *rotlog = nullptr;
-        if (N / 2 <= 1024 && log_entries * sizeof(double2) <= ((size_t)1 << 30) && !getenv("RSVD_B200_JACOBI_INPLACE_V"))
-            rotlog = (double2 *)dalloc_bytes(log_entries * sizeof(double2));
-        void *args[] = {&G, &ldg, &V, &ldv, (void *)&n, (void *)&N, (void *)&tol, &ms, &ctl, &rotlog};
-        cudaError_t e = cudaLaunchCooperativeKernel((void *)jacobi_persistent_kernel, dim3(N / 2), dim3(JT), args, 0, c.stream);
-        if (e == cudaSuccess) {
-            count_launch();
-            RSVD_CUDA(cudaMemcpyAsync(c.h_flag + 16, ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-            RSVD_CUDA(cudaStreamSynchronize(c.stream));
-            dfree(ctl);
-            if (c.h_flag[17]) { set_error("rsvd_b200: Jacobi device-wide barrier timed out"); if (rotlog) dfree(rotlog); return -1; }
-            sweeps = c.h_flag[18];
-            if (rotlog) {
-                if (n <= 1184) launch_replay<4>(V, ldv, n, N, sweeps * (N - 1), rotlog, c.stream);   // <= 2 CTAs per SM, one wave
-                else launch_replay<8>(V, ldv, n, N, sweeps * (N - 1), rotlog, c.stream);
-                count_launch();
-                dfree(rotlog);
-            }
-            if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d (persistent)\n", n, sweeps);
-            return sweeps;
-        }
-        (void)cudaGetLastError();
-        dfree(ctl);
-        if (rotlog) dfree(rotlog);
+    // persistent path: all CTAs co-resident (cooperative launch guarantees it or fails cleanly)
+    static int coop = -1;
+    if (coop < 0) RSVD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
+    if (coop > 0 && !getenv("RSVD_B200_JACOBI_GRAPH")) {
+        static int bw = -1;
+        if (bw < 0) { const char *e = getenv("RSVD_B200_JACOBI_BW"); bw = e ? atoi(e) : 2; }
+        int r;
+        if (n <= JT * 5) r = (bw == 4) ? run_persistent<4, 5>(G, ldg, V, ldv, n, tol, max_sweeps)
+                           : (bw == 1) ? run_persistent<1, 5>(G, ldg, V, ldv, n, tol, max_sweeps)
+                                       : run_persistent<2, 5>(G, ldg, V, ldv, n, tol, max_sweeps);
+        else r = (bw == 1) ? run_persistent<1, 10>(G, ldg, V, ldv, n, tol, max_sweeps)
+                           : run_persistent<2, 10>(G, ldg, V, ldv, n, tol, max_sweeps);
+        if (r >= -1) return r;
     }
 
     // fallback: one kernel per step, a whole sweep replayed from a CUDA graph

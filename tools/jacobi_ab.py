@@ -1,4 +1,5 @@
-"""A/B of the Jacobi V handling (rotation log + replay vs in-place) on a B200: timing and eigenvalue accuracy."""
+"""Timing and accuracy of the one-sided Jacobi kernel on a B200 (run with RSVD_B200_JACOBI_BW=1|2|4 to compare the number of
+columns a CTA rotates between two device-wide barriers)."""
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,9 +16,7 @@ s0 = np.logspace(0, -5, n)
 S = (V0 * s0 ** 2) @ V0.T
 S = (S + S.T) / 2
 R = np.triu(np.linalg.qr((U0 * np.logspace(1, -2.5, n)) @ V0.T)[1])
-for mode in ("log", "inplace", "log"):
-    if mode == "inplace": os.environ["RSVD_B200_JACOBI_INPLACE_V"] = "1"
-    else: os.environ.pop("RSVD_B200_JACOBI_INPLACE_V", None)
+for mode in ("bw=" + os.environ.get("RSVD_B200_JACOBI_BW", "default"),):
     Sd = D.from_numpy_cm(S)
     w = torch.empty(n, dtype=torch.float64, device="cuda")
     native.check(lib.rsvd_b200_eig_small(Sd.data_ptr(), n, n, w.data_ptr())); sync()
