@@ -41,6 +41,23 @@ def test_api_libraries_export_reference_symbols(bits):
         assert hasattr(api.lib, n), n
 
 
+@pytest.mark.parametrize("bits", [32, 64])
+def test_every_symbol_of_the_compiled_reference_is_exported(bits):
+    """A driver written against the reference links against the drop-in whatever subset of the API it uses: the dynamic
+    symbol table of the compiled reference (minus the oracle's own shim symbols) must be a subset of ours."""
+    import subprocess
+    ref = os.path.join(ROOT, "oracle", "_ref", "libref%d.so" % bits)
+    if not os.path.exists(ref):
+        pytest.skip("compiled reference not present")
+    def syms(path):
+        out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+        return {l.split()[2] for l in out.splitlines() if len(l.split()) == 3 and l.split()[1] in "TW"}
+    ours = syms(native.API32_PATH if bits == 32 else native.API64_PATH)
+    theirs = {n for n in syms(ref) if not n.startswith(("oracle_", "vsl", "vsRng", "_"))}
+    assert len(theirs) > 100
+    assert theirs <= ours, sorted(theirs - ours)
+
+
 def test_struct_layout_matches_reference():
     a32, a64 = pkg.Api(32), pkg.Api(64)
     assert C.sizeof(a32.Mat) == 16 and C.sizeof(a32.Vec) == 16    # {int,int,double*}, {int,double*}  (MVH:18-27)
@@ -57,6 +74,16 @@ def test_no_cpu_fallback_fails_loudly():
         api.svd_rand(np.random.rand(30, 20), 4, 2)
     with pytest.raises(RuntimeError):
         api.id_rand(np.random.rand(30, 20), 4, 2, 1, 1)
+    # the baselines and legacy entry points have no host arithmetic behind them either
+    for call in (lambda: api.pqr(np.random.rand(30, 20), 5), lambda: api.svd_decomp(np.random.rand(30, 20), 5, 0.0),
+                 lambda: api.randQB_p(np.random.rand(30, 20), 3, 1), lambda: api.randQB_pb(np.random.rand(30, 20), 2, 2, 1, 1),
+                 lambda: api.svd3(np.random.rand(30, 20), 4, 2, 1), lambda: api.estimate_rank2(np.random.rand(30, 20), 4, 0.1)):
+        call()
+        with pytest.raises(RuntimeError):
+            api.check()
+    from lowrankmatrixdecompositioncodes_b200 import device as D
+    with pytest.raises(RuntimeError):
+        D.load_binary(__file__)
     native.dev().rsvd_b200_clear_error()
 
 
@@ -140,7 +167,8 @@ def test_reference_drivers_relink_unchanged():
     d = os.path.join(ROOT, "oracle", "_ref", "relink")
     if not os.path.isdir(d):
         pytest.skip("relinked drivers not built (reference tree absent)")
-    for name in ["driver_multi_core_mkl1", "driver_multi_core_mkl3", "driver_multi_core_mkl5", "driver1_64bit"]:
+    for name in ["driver_multi_core_mkl1", "driver_multi_core_mkl2", "driver_multi_core_mkl3", "driver_multi_core_mkl4",
+                 "driver_multi_core_mkl5", "driver1_64bit"]:
         exe = os.path.join(d, name)
         assert os.path.exists(exe), name
         out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
