@@ -19,7 +19,8 @@ namespace rsvd {
 namespace {
 
 constexpr int JT = 128;     // threads per pair
-constexpr int JR = 10;      // rows per thread: supports n <= 1280
+constexpr int JR = 10;      // rows per thread of the graph fallback: n <= 1280
+constexpr int JMAX = 2048;  // persistent path: 256 threads x 8 rows per column and 1024 pair slots in the replay kernel
 
 __device__ __forceinline__ double block_sum3(double &a, double &b, double &c, double *sh) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -178,22 +179,22 @@ __device__ __forceinline__ void rot_params(double a, double b, double c, double 
     sn = cs * t;
 }
 
-template <int K>
-__device__ __forceinline__ void block_sumK(double (&v)[K], double *sh) {   // sh: K * (JT/32) doubles, one __syncthreads
+template <int K, int NT>
+__device__ __forceinline__ void block_sumK(double (&v)[K], double *sh) {   // sh: K * (NT/32) doubles, one __syncthreads
 #pragma unroll
     for (int e = 0; e < K; ++e)
         for (int o = 16; o > 0; o >>= 1) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (l == 0) {
 #pragma unroll
-        for (int e = 0; e < K; ++e) sh[e * (JT / 32) + w] = v[e];
+        for (int e = 0; e < K; ++e) sh[e * (NT / 32) + w] = v[e];
     }
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < K; ++e) {
         double t = 0.0;
 #pragma unroll
-        for (int i = 0; i < JT / 32; ++i) t += sh[e * (JT / 32) + i];
+        for (int i = 0; i < NT / 32; ++i) t += sh[e * (NT / 32) + i];
         v[e] = t;
     }
 }
@@ -201,12 +202,11 @@ __device__ __forceinline__ void block_sumK(double (&v)[K], double *sh) {   // sh
 // ctl[0] = barrier counter, ctl[1] = error flag, ctl[2] = sweeps done, ctl[8 + s] = CTAs that rotated in sweep s,
 // (unsigned long long *)(ctl + 4)[0] = bit pattern of the largest |cosine| met in the current sweep (positive doubles order like integers)
 // The rotations are only LOGGED (rotlog[step][slot] = (c, s), identity when nothing was rotated): V is rebuilt afterwards by
-// jacobi_replay_kernel, off the critical path.  RPT = rows per thread (JT*RPT >= n).
-template <int BW, int RPT>
-__global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ldg, int n, int NBk, double tol, int max_sweeps, int *ctl,
+// jacobi_replay_kernel, off the critical path.  NT threads per CTA, RPT rows per thread (NT*RPT >= n).
+template <int BW, int RPT, int NT>
+__global__ void __launch_bounds__(NT) jacobi_persistent_kernel(double *G, i64 ldg, int n, int NBk, double tol, int max_sweeps, int *ctl,
                                                                double2 *rotlog) {
-    __shared__ double sh[2][3 * BW * (JT / 32) > 2 * BW * (JT / 32) ? 3 * BW * (JT / 32) : 2 * BW * (JT / 32)];
-    const int i = blockIdx.x;
+    __shared__ double sh[2][2 * BW * (NT / 32)];
     const int N = NBk * BW, half = N / 2;
     int gen = 0, shb = 0;
     unsigned long long *maxcos = reinterpret_cast<unsigned long long *>(ctl + 4);
@@ -215,6 +215,10 @@ __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ld
         int rotated = 0;
         double cmax = 0.0;
         for (int rb = 0; rb < NBk - 1; ++rb) {
+          const i64 gs_round = gs;
+          // one slot per CTA when the grid covers the tournament (n <= ~1184); larger problems stride over the slots
+          for (int i = blockIdx.x; i < NBk / 2; i += gridDim.x) {
+            gs = gs_round;
             int P, Q;
             block_pair(NBk, rb, i, P, Q);
             // ---- load the 2*BW columns and their squared norms
@@ -227,13 +231,13 @@ __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ld
                 double a = 0.0;
 #pragma unroll
                 for (int k = 0; k < RPT; ++k) {
-                    const int row = threadIdx.x + k * JT;
+                    const int row = threadIdx.x + k * NT;
                     X[cc][k] = (row < n && col[cc] < n) ? __ldcg(g + row) : 0.0;   // L2 loads: other SMs wrote these columns in the previous round
                     a = fma(X[cc][k], X[cc][k], a);
                 }
                 nrm[cc] = a;
             }
-            block_sumK<2 * BW>(nrm, sh[shb]); shb ^= 1;
+            block_sumK<2 * BW, NT>(nrm, sh[shb]); shb ^= 1;
             bool dirty[2 * BW];
 #pragma unroll
             for (int cc = 0; cc < 2 * BW; ++cc) dirty[cc] = false;
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ld
                     for (int k = 0; k < RPT; ++k) c = fma(X[ca[j]][k], X[cb[j]][k], c);
                     dots[j] = c;
                 }
-                block_sumK<BW>(dots, sh[shb]); shb ^= 1;
+                block_sumK<BW, NT>(dots, sh[shb]); shb ^= 1;
 #pragma unroll
                 for (int j = 0; j < BW; ++j) {
                     const double a = nrm[ca[j]], b = nrm[cb[j]], c = dots[j];
@@ -288,11 +292,12 @@ __global__ void __launch_bounds__(JT) jacobi_persistent_kernel(double *G, i64 ld
                     double *g = G + (i64)col[cc] * ldg;
 #pragma unroll
                     for (int k = 0; k < RPT; ++k) {
-                        const int row = threadIdx.x + k * JT;
+                        const int row = threadIdx.x + k * NT;
                         if (row < n) g[row] = X[cc][k];
                     }
                 }
             }
+          }
             if (rb == NBk - 2 && rotated && threadIdx.x == 0) {
                 atomicAdd(ctl + 8 + sweep, 1);
                 atomicMax(maxcos + (sweep & 1), (unsigned long long)__double_as_longlong(cmax));
@@ -376,23 +381,24 @@ static void launch_replay(double *V, i64 ldv, int n, int NBk, i64 steps, const d
 }
 
 // one (BW, RPT) instantiation of the persistent path; returns sweeps, -1 on a barrier time-out, -2 when it could not launch
-template <int BW, int RPT>
+template <int BW, int RPT, int NT = JT>
 static int run_persistent(double *G, i64 ldg, double *V, i64 ldv, int n, double tol, int max_sweeps) {
     Ctx &c = ctx();
     static int blocks_per_sm = -1;
-    if (blocks_per_sm < 0) RSVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_persistent_kernel<BW, RPT>, JT, 0));
+    if (blocks_per_sm < 0) RSVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_persistent_kernel<BW, RPT, NT>, NT, 0));
     int NBk = 2 * ((n + 2 * BW - 1) / (2 * BW));
     const int N = NBk * BW, half = N / 2;
-    if (NBk / 2 > blocks_per_sm * c.sms || half > 1024) return -2;
+    if (half > 1024 || blocks_per_sm < 1) return -2;
+    const int grid = std::min(NBk / 2, blocks_per_sm * c.sms);
     const size_t log_entries = (size_t)max_sweeps * (N - 1) * half;
-    if (log_entries * sizeof(double2) > ((size_t)1 << 30)) return -2;
+    if (log_entries * sizeof(double2) > ((size_t)3 << 30)) return -2;
     int *ctl = (int *)dalloc_bytes(64 * sizeof(int));
     double2 *rotlog = (double2 *)dalloc_bytes(log_entries * sizeof(double2));
     if (g_status) return -2;
     RSVD_CUDA(cudaMemsetAsync(ctl, 0, 64 * sizeof(int), c.stream));
     int ms = max_sweeps;
     void *args[] = {&G, &ldg, (void *)&n, &NBk, (void *)&tol, &ms, &ctl, &rotlog};
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)jacobi_persistent_kernel<BW, RPT>, dim3(NBk / 2), dim3(JT), args, 0, c.stream);
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)jacobi_persistent_kernel<BW, RPT, NT>, dim3(grid), dim3(NT), args, 0, c.stream);
     int sweeps = -2;
     if (e == cudaSuccess) {
         count_launch();
@@ -446,7 +452,7 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
     if (g_status) return -1;   // an earlier error is pending: launch nothing
     set_identity(V, ldv, n);
     const int N = (n + 1) & ~1;
-    if (n > JT * JR) { set_error("rsvd_b200: Jacobi kernel supports n <= %d (got %d)", JT * JR, n); return -1; }
+    if (n > JMAX) { set_error("rsvd_b200: Jacobi kernel supports n <= %d (got %d)", JMAX, n); return -1; }
     if (n < 2) return 0;
     const double tol = 2.220446049250313e-16 * sqrt((double)n);
     const int max_sweeps = 40;
@@ -462,10 +468,12 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
         if (n <= JT * 5) r = (bw == 4) ? run_persistent<4, 5>(G, ldg, V, ldv, n, tol, max_sweeps)
                            : (bw == 1) ? run_persistent<1, 5>(G, ldg, V, ldv, n, tol, max_sweeps)
                                        : run_persistent<2, 5>(G, ldg, V, ldv, n, tol, max_sweeps);
-        else r = (bw == 1) ? run_persistent<1, 10>(G, ldg, V, ldv, n, tol, max_sweeps)
-                           : run_persistent<2, 10>(G, ldg, V, ldv, n, tol, max_sweeps);
+        else if (n <= JT * 10) r = (bw == 1) ? run_persistent<1, 10>(G, ldg, V, ldv, n, tol, max_sweeps)
+                                             : run_persistent<2, 10>(G, ldg, V, ldv, n, tol, max_sweeps);
+        else r = run_persistent<2, 8, 256>(G, ldg, V, ldv, n, tol, max_sweeps);     // 256 threads x 8 rows: 2 CTAs per SM stay co-resident
         if (r >= -1) return r;
     }
+    if (n > JT * JR) { set_error("rsvd_b200: Jacobi of n = %d needs the persistent kernel (cooperative launch and a rotation log of %.1f GB)", n, 40.0 * n * n / 2 * 16 / 1e9); return -1; }
 
     // fallback: one kernel per step, a whole sweep replayed from a CUDA graph
     int *flag = c.d_flag + 16;
@@ -517,32 +525,55 @@ void jacobi_svd(double *A, i64 lda, i64 n_, double *U, i64 ldu, double *s, doubl
     dfree(dperm);
 }
 
-// eigenvalue sign: lambda_j = sigma_j * sign(u_j . v_j)
-__global__ void eig_sign_kernel(const double *U, i64 ldu, const double *Vt, i64 ldvt, int n, double *w) {
-    const int lane = threadIdx.x & 31;
-    int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j >= n) return;
-    double s = 0.0;
-    for (int r = lane; r < n; r += 32) s = fma(U[(i64)j * ldu + r], Vt[(i64)r * ldvt + j], s);
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0 && s < 0.0) w[j] = -w[j];
+// ---- symmetric eigenproblem (dsyev 'V','U' of MVF:1206-1209, called on B*B^T at RRA:190) -------------------------------
+// One-sided Jacobi applied to S itself needs a number of sweeps that grows with cond(S) — and S = B B^T carries the SQUARED
+// spectrum (40 sweeps and still 1e-11 absolute error at cond 1e10).  Preconditioned as in Drmac-Veselic: S P = Q R by the
+// column-pivoted QR kernel, then Jacobi on the lower-triangular R^T, which is nearly diagonal and converges in a few sweeps:
+//   R^T = U1 Sigma V1^T  =>  S = (Q V1) Sigma (P U1)^T,
+// so the eigenvectors are the rows of U1 scattered by the permutation (W = P U1; Q is never formed) and the eigenvalues are
+// Sigma with the sign of the Rayleigh quotient w_j^T S w_j (B B^T is PSD; the sign keeps the routine valid for indefinite S).
+// W(jp[i], j) = U1(i, j)
+__global__ void scatter_rows_kernel(const double *__restrict__ U1, i64 ldu, const double *__restrict__ jp, int n, double *W, i64 ldw) {
+    const int j = blockIdx.x;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) W[(i64)j * ldw + (i64)jp[i]] = U1[(i64)j * ldu + i];
 }
-// ascending reorder: Aout(:, j) = Vt(n-1-j, :)^T ; wout[j] = w[n-1-j]   (valid for the PSD matrices of the hot path)
-__global__ void eig_reverse_kernel(const double *Vt, i64 ldvt, const double *w, int n, double *A, i64 lda, double *wout) {
+// ascending order: A(:, j) = W(:, n-1-j), w[j] = sign(W(:,src) . T(:,src)) * s[src],  T = S W
+__global__ void eig_finish_kernel(const double *__restrict__ W, i64 ldw, const double *__restrict__ T, i64 ldt, const double *__restrict__ s, int n,
+                                  double *A, i64 lda, double *wout) {
+    __shared__ double sh[4];
     const int j = blockIdx.x, src = n - 1 - j;
-    for (int r = threadIdx.x; r < n; r += blockDim.x) A[(i64)j * lda + r] = Vt[(i64)r * ldvt + src];
-    if (threadIdx.x == 0) wout[j] = w[src];
+    double d = 0.0;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const double v = W[(i64)src * ldw + r];
+        A[(i64)j * lda + r] = v;
+        d = fma(v, T[(i64)src * ldt + r], d);
+    }
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+        wout[j] = (t < 0.0) ? -s[src] : s[src];
+    }
 }
 
 void jacobi_eig(double *A, i64 lda, i64 n_, double *w) {
     ensure_init();
     Ctx &c = ctx();
     const int n = (int)n_;
-    if (n <= 0) return;
-    DBuf U((size_t)n * n), Vt((size_t)n * n), s((size_t)n);
-    jacobi_svd(A, lda, n, U.p, n, s.p, Vt.p, n);
-    eig_sign_kernel<<<(n * 32 + 255) / 256, 256, 0, c.stream>>>(U.p, n, Vt.p, n, n, s.p);
-    eig_reverse_kernel<<<n, 128, 0, c.stream>>>(Vt.p, n, s.p, n, A, lda, w);
+    if (n <= 0 || g_status) return;
+    DBuf S0((size_t)n * n), Rt((size_t)n * n), U1((size_t)n * n), Vt((size_t)n * n), s((size_t)n), jp((size_t)n), W((size_t)n * n);
+    copy_matrix(A, lda, S0.p, n, n, n);
+    geqp3(A, lda, n, n, jp.p);                       // S P = Q R, R in the upper triangle of A
+    keep_upper(A, lda, n);
+    transpose(A, lda, Rt.p, n, n, n);                // R^T, lower triangular with a decreasing diagonal
+    jacobi_svd(Rt.p, n, n, U1.p, n, s.p, Vt.p, n);
+    scatter_rows_kernel<<<n, 128, 0, c.stream>>>(U1.p, n, jp.p, n, W.p, n);
+    Gemm g;
+    g.ta = 'N'; g.tb = 'N'; g.m = n; g.n = n; g.k = n; g.A = S0.p; g.lda = n; g.B = W.p; g.ldb = n; g.C = Rt.p; g.ldc = n;   // T = S W (reuses Rt)
+    gemm(g);
+    eig_finish_kernel<<<n, 128, 0, c.stream>>>(W.p, n, Rt.p, n, s.p, n, A, lda, w);
     count_launch(2);
 }
 

@@ -132,7 +132,7 @@ def test_orthonormalize(lib, m, l, cond, force):
         assert np.linalg.norm(Q - Qh @ (Qh.T @ Q)) < 1e-6
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 33, 120, 520])
+@pytest.mark.parametrize("n", [1, 2, 5, 33, 120, 520, 1500])
 def test_jacobi_svd_and_eig(lib, n):
     rng = np.random.default_rng(n)
     U0, _ = np.linalg.qr(rng.standard_normal((n, n)))
