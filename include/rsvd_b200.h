@@ -118,6 +118,11 @@ int rsvd_b200_id_two_sided_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsv
 /* cur_rand_decomp_fixed_rank (RRA:2191-2258). C m x k, U k x k, R k x n. */
 int rsvd_b200_cur_rand_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 k, rsvd_i64 p, int q, int s,
                            uint64_t seed, double *C, rsvd_i64 ldc, double *U, rsvd_i64 ldu, double *R, rsvd_i64 ldr);
+/* Introspection (host only, no GPU needed): the column-pair schedule of the one-sided Jacobi kernel for an n x n problem with
+ * blocks of bw columns (1, 2 or 4).  Returns N = n rounded up to a multiple of 2*bw; with pairs != NULL fills
+ * pairs[(step*(N/2) + slot)*2 + {0,1}] for the N-1 steps of a sweep.  Every pair of columns must meet exactly once. */
+int rsvd_b200_jacobi_schedule(int n, int bw, int *pairs);
+
 /* ---- binary matrix files <-> device memory ----
  * The reference's format (MVF:77-133; 64-bit MVF64:78-135): two int32 (index_bits = 32) or int64 (64) m, n, then ROW-major
  * doubles.  Row blocks are DMA'd as they lie in the file and transposed on the device; the host never holds the matrix.

@@ -12,6 +12,7 @@ int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, i
            i64 ldq, double *B, i64 ldb, i64 max_rank, i64 *frank_out, int legacy_reorth);
 int randqb_single(double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, uint64_t seed, double *Q, i64 ldq, double *B, i64 ldb);
 int svd_full(const double *A, i64 m, i64 n, i64 lda, double *U, i64 ldu, double *S, double *V, i64 ldv);
+int jacobi_schedule(int n, int bw, int *pairs);
 int estimate_rank1(const double *A, i64 m, i64 n, i64 lda, i64 maxdim, double tol, uint64_t seed, double *Q, i64 ldq, i64 *rank_out);
 int estimate_rank2(const double *A, i64 m, i64 n, i64 lda, i64 kblock, double tol, uint64_t seed, double *Y, i64 ldy, double *Q, i64 ldq,
                    i64 max_cols, i64 *rank_out);
@@ -179,6 +180,8 @@ int rsvd_b200_svd_full_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda
     READY();
     return finish(svd_full(A, m, n, lda, U, ldu, S, V, ldv));
 }
+
+int rsvd_b200_jacobi_schedule(int n, int bw, int *pairs) { return jacobi_schedule(n, bw, pairs); }
 
 int rsvd_b200_estimate_rank1_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, rsvd_i64 maxdim, double tol, uint64_t seed, double *Q,
                                  rsvd_i64 ldq, rsvd_i64 *rank) {

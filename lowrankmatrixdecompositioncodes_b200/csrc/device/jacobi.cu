@@ -114,14 +114,14 @@ __device__ __forceinline__ bool grid_barrier(int *bar, int gen, int *err) {
 //   then, per tournament round : BW steps pairing column j of block P with column (j + t) mod BW of block Q, t = 0..BW-1,
 // so a CTA rotates 2*BW register-resident columns BW times between two device-wide barriers instead of once.
 // BW = 1 is the plain round-robin of column pairs.  Pair slot of (CTA i, pair j) = i*BW + j.
-__device__ __forceinline__ void block_pair(int NBk, int rb, int i, int &P, int &Q) {
+__host__ __device__ __forceinline__ void block_pair(int NBk, int rb, int i, int &P, int &Q) {
     const int M = NBk - 1;
     if (i == 0) { P = M; Q = rb; }
     else { P = (rb + i) % M; Q = (rb - i + M) % M; }
 }
 // local (register) column indices of pair j at intra-block step t: 0..BW-1 = block P, BW..2BW-1 = block Q
 template <int BW>
-__device__ __forceinline__ void intra_pair(int t, int j, int &ca, int &cb) {
+__host__ __device__ __forceinline__ void intra_pair(int t, int j, int &ca, int &cb) {
     const int off = (j < BW / 2) ? 0 : BW, jj = (j < BW / 2) ? j : j - BW / 2;
     int x, y;
     if (jj == 0) { x = BW - 1; y = t; }
@@ -130,7 +130,7 @@ __device__ __forceinline__ void intra_pair(int t, int j, int &ca, int &cb) {
 }
 // global column indices (p, q) of pair slot (i, j) at sweep-local step st
 template <int BW>
-__device__ __forceinline__ void pair_at(int NBk, int st, int i, int j, int &p, int &q) {
+__host__ __device__ __forceinline__ void pair_at(int NBk, int st, int i, int j, int &p, int &q) {
     int P, Q;
     if (BW > 1 && st < BW - 1) {
         block_pair(NBk, 0, i, P, Q);
@@ -575,6 +575,25 @@ void jacobi_eig(double *A, i64 lda, i64 n_, double *w) {
     gemm(g);
     eig_finish_kernel<<<n, 128, 0, c.stream>>>(W.p, n, Rt.p, n, s.p, n, A, lda, w);
     count_launch(2);
+}
+
+// Host-side evaluation of the pair schedule the kernels use (same inline functions), for tests: pairs[(st*(N/2) + slot)*2 + {0,1}]
+// for the N-1 steps of one sweep; returns N (n rounded up to a multiple of 2*bw), or 0 for an unsupported bw.
+template <int BW>
+static int schedule_host(int n, int *pairs) {
+    const int NBk = 2 * ((n + 2 * BW - 1) / (2 * BW)), N = NBk * BW;
+    if (pairs)
+        for (int st = 0; st < N - 1; ++st)
+            for (int slot = 0; slot < N / 2; ++slot) {
+                int p, q;
+                pair_at<BW>(NBk, st, slot / BW, slot % BW, p, q);
+                pairs[((size_t)st * (N / 2) + slot) * 2] = p;
+                pairs[((size_t)st * (N / 2) + slot) * 2 + 1] = q;
+            }
+    return N;
+}
+int jacobi_schedule(int n, int bw, int *pairs) {
+    return bw == 1 ? schedule_host<1>(n, pairs) : bw == 2 ? schedule_host<2>(n, pairs) : bw == 4 ? schedule_host<4>(n, pairs) : 0;
 }
 
 }  // namespace rsvd

@@ -65,6 +65,7 @@ SIGNATURES = {
     "rsvd_b200_svd_from_qb_dev": (C.c_int, [dp, i64, i64, dp, i64, i64, i64, dp, i64, dp, dp, i64]),
     "rsvd_b200_id_two_sided_rand_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, dp, dp, dp, i64, dp, i64]),
     "rsvd_b200_cur_rand_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, dp, i64, dp, i64, dp, i64]),
+    "rsvd_b200_jacobi_schedule": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "rsvd_b200_load_binary_dev": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(i64)]),
     "rsvd_b200_store_binary_dev": (C.c_int, [C.c_char_p, C.c_int, dp, i64, i64, i64]),
     "rsvd_b200_randqb_legacy_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, dp, i64, dp, i64]),

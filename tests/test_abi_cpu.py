@@ -174,3 +174,20 @@ def test_reference_drivers_relink_unchanged():
         out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
         assert "not found" not in out, out
         assert "librsvd_b200" in out
+
+
+@pytest.mark.parametrize("n,bw", [(2, 1), (7, 1), (520, 1), (3, 2), (10, 2), (520, 2), (1050, 2), (9, 4), (520, 4), (64, 4)])
+def test_jacobi_pair_schedule_is_a_complete_tournament(n, bw):
+    """Host logic of the Jacobi kernels (csrc/device/jacobi.cu: block_pair / intra_pair / pair_at, shared by the rotation
+    kernel and the replay kernel): in one sweep every pair of columns meets exactly once and the pairs of a step are disjoint."""
+    lib = native.dev()
+    N = lib.rsvd_b200_jacobi_schedule(n, bw, None)
+    assert N >= n and N % (2 * bw) == 0 and N - n < 2 * bw
+    buf = (C.c_int * ((N - 1) * (N // 2) * 2))()
+    assert lib.rsvd_b200_jacobi_schedule(n, bw, buf) == N
+    pairs = np.frombuffer(buf, dtype=np.int32).reshape(N - 1, N // 2, 2)
+    assert pairs.min() == 0 and pairs.max() == N - 1
+    for st in range(N - 1):
+        assert len(set(pairs[st].ravel().tolist())) == N          # disjoint: all N columns appear once
+    met = {(min(p, q), max(p, q)) for p, q in pairs.reshape(-1, 2).tolist()}
+    assert len(met) == N * (N - 1) // 2 and all(p != q for p, q in met)
