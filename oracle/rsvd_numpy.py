@@ -305,6 +305,151 @@ def id_rand_decomp_fromQB(Q, B):
 # ------------------------------------------------------------------------------------------------
 # synthetic inputs + binary file formats
 # ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# deterministic baselines and legacy entry points
+# ------------------------------------------------------------------------------------------------
+def pivoted_QR_of_specified_rank_or_prec(M, k, TOL=None):
+    """RRA:1159-1334 (TOL given) / RRA:1012-1155 (TOL None): the reference's OWN partial Householder QR.
+    Squared column norms (MVF:445-454), first index of the maximum by strict '>', reflector v = x - ||x|| e_i scaled to
+    ||v||^2 = 2 (RRA:982-1008, so R(i,i) = +||x||), plain downdate norm -= R(i,j)^2 (RRA:1316-1319); stop when the largest
+    remaining squared norm is 0 (fixed-rank variant, RRA:1066) / below 1e-10 in magnitude (RRA:1269) for i > 0, or — tolerance
+    mode, k <= 0 — when sqrt(sum of remaining squared norms)/n, refreshed every 5th step only, is below TOL (RRA:1243-1275).
+    Returns frank, Qk (m x frank), Rk (frank x n), I (n, 0-based)."""
+    m, n = M.shape
+    tol_mode = k <= 0
+    kmax = min(m, n) if tol_mode else min(k, min(m, n))
+    R = np.array(M, dtype=np.float64, order="F")
+    Q = np.eye(m)
+    norms = np.sum(R * R, axis=0)
+    I = np.arange(n, dtype=np.float64)
+    frank, r22 = 0, 0.0
+    for i in range(kmax):
+        j = i + int(np.argmax(norms[i:]))                   # first index of the maximum
+        if i % 5 == 0:
+            r22 = np.sqrt(np.sum(norms[i:])) / n if tol_mode else 0.0
+        zero = (norms[j] == 0.0) if TOL is None else (abs(norms[j]) < 1e-10)
+        if zero and i > 0:
+            break
+        if tol_mode and TOL is not None and r22 < TOL:
+            break
+        frank = i + 1
+        I[[i, j]] = I[[j, i]]
+        R[:, [i, j]] = R[:, [j, i]]
+        norms[[i, j]] = norms[[j, i]]
+        v = np.zeros(m)
+        v[i:] = R[i:, i]
+        v[i] -= np.linalg.norm(R[i:, i])
+        nv = np.linalg.norm(v)
+        if nv > 0:
+            v *= np.sqrt(2.0) / nv
+        R -= np.outer(v, v @ R)
+        Q -= np.outer(Q @ v, v)
+        if i != n - 1:
+            norms[i + 1:] -= R[i, i + 1:] ** 2
+    return frank, Q[:, :frank].copy(), R[:frank, :].copy(), I
+
+
+def id_decomp_fixed_rank_or_prec(M, k, TOL):
+    """RRA:1807-1854: partial pivoted QR when k < min(m,n) (or tolerance mode), dgeqp3 otherwise; T = triu(Rk1)^{-1} Rk2."""
+    m, n = M.shape
+    if k < min(m, n):
+        frank, _, Rk, I = pivoted_QR_of_specified_rank_or_prec(M, k, TOL)
+    else:
+        frank = k
+        Rk, I = pivotedQR_mkl(M)
+    T = upper_triangular_system_solve(np.triu(Rk[:frank, :frank]), Rk[:frank, frank:])
+    return frank, I, T
+
+
+def id_two_sided_decomp_fixed_rank_or_prec(M, k, TOL):
+    """RRA:2034-2056"""
+    frank, Icol, T = id_decomp_fixed_rank_or_prec(M, k, TOL)
+    MI = M[:, Icol[:frank].astype(int)]
+    frank, Irow, S = id_decomp_fixed_rank_or_prec(np.ascontiguousarray(MI.T), frank, 0.0)
+    return frank, Icol, Irow, T, S
+
+
+def low_rank_svd_decomp_fixed_rank_or_prec(M, k, TOL):
+    """RRA:7-69: dgesvd, then truncation to k or — k <= 0 — to the first i with abs((int)sigma_i) < TOL (the C integer abs
+    of RRA:49)."""
+    U, s, Vt = np.linalg.svd(M, full_matrices=False)
+    r = len(s)
+    frank = k if k > 0 else r
+    if k <= 0:
+        for i in range(r):
+            if abs(int(s[i])) < TOL and i < r - 1:
+                frank = i + 1
+                break
+    return frank, U[:, :frank], np.diag(s[:frank]), Vt[:frank].T
+
+
+def randQB_p(M, k, p, seed=777):
+    """RRA:1343-1421: single-vector randQB; the Gram-Schmidt loop runs over i < j-1 (RRA:1387)."""
+    m, n = M.shape
+    RN = initialize_random_matrix(n, k, seed)
+    A = np.array(M, dtype=np.float64)
+    Q, B = np.zeros((m, k)), np.zeros((k, n))
+    for j in range(k):
+        y = A @ RN[:, j]
+        for _ in range(p):
+            y = A @ (A.T @ y)
+        for i in range(j - 1):
+            y = y - (Q[:, i] @ y) * Q[:, i]
+        q = y / np.linalg.norm(y)
+        b = A.T @ q
+        Q[:, j], B[j] = q, b
+        A -= np.outer(q, b)
+    return Q, B
+
+
+def randQB_pb(M, kstep, nstep, p, s, seed=777):
+    """RRA:1425-1572: blocked randQB, power loop j <= p, re-orthogonalisation against all previous blocks on EVERY step > 0."""
+    m, n = M.shape
+    l = kstep * nstep
+    RN = initialize_random_matrix(n, l, seed)
+    A = np.array(M, dtype=np.float64)
+    Q, B = np.zeros((m, l)), np.zeros((l, n))
+    for step in range(nstep):
+        sl = slice(kstep * step, kstep * (step + 1))
+        Yp = A @ RN[:, sl]
+        for j in range(1, p + 1):
+            W = A.T @ (QR_factorization_getQ(Yp) if (2 * j - 2) % s == 0 else Yp)
+            Yp = A @ (QR_factorization_getQ(W) if (2 * j - 1) % s == 0 else W)
+        Qp = QR_factorization_getQ(Yp)
+        if step > 0:
+            Qj = Q[:, :kstep * step]
+            Qp = QR_factorization_getQ(Qp - Qj @ (Qj.T @ Qp))
+        Bp = Qp.T @ A
+        A -= Qp @ Bp
+        Q[:, sl], B[sl] = Qp, Bp
+    return Q, B
+
+
+def estimate_rank_and_buildQ(M, frac_of_max_rank, TOL, seed=777):
+    """MVF:1339-1400: Y = M RN, sequential modified Gram-Schmidt; stop at column j when two consecutive projections (p1
+    persists across columns, starts at 0) are both shorter than TOL; Q = orthonormal basis of the first good_rank columns."""
+    m, n = M.shape
+    maxdim = int(round(min(m, n) * frac_of_max_rank))
+    Qb = M @ initialize_random_matrix(n, maxdim, seed)
+    good, p1 = maxdim, 0.0
+    stop = False
+    for j in range(maxdim):
+        vj = Qb[:, j].copy()
+        for i in range(j):
+            vi = Qb[:, i]
+            coef = (vj @ vi) / (vi @ vi)
+            vj -= coef * vi
+            pn = abs(coef) * np.linalg.norm(vi)
+            if pn < TOL and p1 < TOL:
+                good, stop = j, True
+                break
+            p1 = pn
+        if stop:
+            break
+        Qb[:, j] = vj / np.linalg.norm(vj)
+    return good, QR_factorization_getQ(Qb[:, :good])
+
+
 def make_matrix(m, n, spectrum="logspace", seed=0, k=None, tail=1e-8, rho=1.0 / 1.02):
     """make_matrix_binary.m:11-25 — A = U diag(sigma) V^T with Haar U, V.
     spectrum: 'logspace' (the reference's logspace(1,-3,p)), 'exp' (sigma_i = rho^i, the oneAPI

@@ -52,5 +52,37 @@ def main():
     print("wrote golden_small.npz with", len(out), "arrays")
 
 
+def main_baselines():
+    """tests/golden/golden_baselines.npz: deterministic baselines and legacy entry points."""
+    L = ref_lib.RefLib(32)
+    out = {}
+    A, _ = O.make_matrix(60, 40, "logspace", seed=3)
+    out["A"] = A
+    f, Q, R, I = L.pqr(A, 10)
+    out["pqr_k10_frank"], out["pqr_k10_Q"], out["pqr_k10_R"], out["pqr_k10_I"] = np.array(f), Q, R, I
+    f, Q, R, I = L.pqr(A, 0, 0.05)
+    out["pqr_tol_frank"], out["pqr_tol_R"], out["pqr_tol_I"] = np.array(f), R, I
+    f, I, T = L.id_decomp(A, 12, 0.0)
+    out["id_k12_frank"], out["id_k12_I"], out["id_k12_T"] = np.array(f), I, T
+    f, Ic, Ir, T, S = L.id_two_sided_decomp(A, 0, 0.05)
+    out["id2_tol_frank"], out["id2_tol_Icol"], out["id2_tol_Irow"], out["id2_tol_T"], out["id2_tol_S"] = np.array(f), Ic, Ir, T, S
+    f, Cm, U, R = L.cur_decomp(A, 9, 0.0)
+    out["cur_k9_C"], out["cur_k9_U"], out["cur_k9_R"] = Cm, U, R
+    f, U, S, V = L.svd_decomp(A, 7, 0.0)
+    out["svd_k7_S"] = S
+    out["svd_tol_frank"] = np.array(L.svd_decomp(A, 0, 2.0)[0])
+    Q, B = L.randQB_p(A, 6, 1, seed=777)
+    out["qbp_Q"], out["qbp_B"] = Q, B
+    Q, B = L.randQB_pb(A, 4, 3, 1, 1, seed=777)
+    out["qbpb_QB"] = Q @ B
+    for name, args in [("svd1", (8,)), ("svd2", (8,)), ("svd3", (8, 3, 1)), ("svd4", (4, 2, 1))]:
+        U, S, V = getattr(L, name)(A, *args, seed=777)
+        out[name + "_S"] = S
+    out["rank1"] = np.array(L.estimate_rank1(A, 0.5, 1e-3, seed=777)[0])
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), "golden_baselines.npz"), **out)
+    print("wrote golden_baselines.npz with", len(out), "arrays")
+
+
 if __name__ == "__main__":
     main()
+    main_baselines()

@@ -283,3 +283,35 @@ def test_baselines_through_the_int64_abi(api):
     assert relerr(Qb @ Bb, Q0 @ B0) < 1e-9
     fr, U, S_, V = api64.svd_decomp(A, 20, 0.0)
     assert fr == 20 and np.max(np.abs(np.diag(S_) - np.linalg.svd(A, compute_uv=False)[:20])) < 1e-13
+
+
+def test_baselines_vs_committed_golden_vectors(api):
+    """Same checks against tests/golden/golden_baselines.npz (outputs of the compiled reference, committed): runs even where
+    oracle/_ref is absent."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_baselines.npz"))
+    A = g["A"]
+    f, Q, R, I = api.pqr(A, 10)
+    assert f == int(g["pqr_k10_frank"]) and np.array_equal(I, g["pqr_k10_I"])
+    assert relerr(R, g["pqr_k10_R"]) < 1e-10 and relerr(Q, g["pqr_k10_Q"]) < 1e-10
+    f, Q, R, I = api.pqr(A, 0, 0.05)
+    assert f == int(g["pqr_tol_frank"]) and np.array_equal(I, g["pqr_tol_I"]) and relerr(R, g["pqr_tol_R"]) < 1e-10
+    f, I, T = api.id_decomp(A, 12, 0.0)
+    assert f == int(g["id_k12_frank"]) and np.array_equal(I, g["id_k12_I"]) and relerr(T, g["id_k12_T"]) < 1e-9
+    f, Ic, Ir, T, S = api.id_two_sided_decomp(A, 0, 0.05)
+    assert f == int(g["id2_tol_frank"]) and np.array_equal(Ic, g["id2_tol_Icol"]) and np.array_equal(Ir, g["id2_tol_Irow"])
+    assert relerr(T, g["id2_tol_T"]) < 1e-9 and relerr(S, g["id2_tol_S"]) < 1e-9
+    f, Cm, U, R = api.cur_decomp(A, 9, 0.0)
+    assert np.array_equal(Cm, g["cur_k9_C"]) and np.array_equal(R, g["cur_k9_R"])
+    assert relerr(Cm @ U @ R, g["cur_k9_C"] @ g["cur_k9_U"] @ g["cur_k9_R"]) < 1e-8
+    assert rel_sigma_err(api.svd_decomp(A, 7, 0.0)[2], g["svd_k7_S"]) < 1e-12
+    assert api.svd_decomp(A, 0, 2.0)[0] == int(g["svd_tol_frank"])
+    Q, B = api.randQB_p(A, 6, 1, seed=777)
+    assert relerr(Q, g["qbp_Q"]) < 1e-9 and relerr(B, g["qbp_B"]) < 1e-9
+    Q, B = api.randQB_pb(A, 4, 3, 1, 1, seed=777)
+    assert relerr(Q @ B, g["qbpb_QB"]) < 1e-10
+    for name, args, tol in [("svd1", (8,), 1e-7), ("svd2", (8,), 1e-10), ("svd3", (8, 3, 1), 1e-10), ("svd4", (4, 2, 1), 1e-7)]:
+        S = getattr(api, name)(A, *args, seed=777)[1]
+        assert np.max(np.abs(np.diag(S) - np.diag(g[name + "_S"]))) / np.diag(g[name + "_S"]).max() < tol, name
+    assert api.estimate_rank1(A, 0.5, 1e-3, seed=777)[0] == int(g["rank1"])
+    api.check()

@@ -105,3 +105,74 @@ def test_binary_io_formats_roundtrip_with_reference(ref32, tmp_path):
     ref32.lib.matrix_delete(M)
     assert np.array_equal(O.read_matrix_binary(g, 32), A)
     assert open(f, "rb").read() == open(g, "rb").read()
+
+
+# ---- twins of the deterministic baselines / legacy entry points, pinned against the compiled reference --------------------
+def _decaying(m, n, r, lo=-6, seed=0):
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.standard_normal((m, r)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, r)))
+    return (U * np.logspace(0, lo, r)) @ V.T
+
+
+@pytest.mark.parametrize("m,n,r,k,TOL", [(60, 80, 25, 10, None), (90, 70, 40, 20, 0.0), (80, 120, 50, 0, 1e-4), (50, 40, 6, 20, 0.0)])
+def test_twin_partial_pivoted_qr_matches_reference(ref32, m, n, r, k, TOL):
+    A = _decaying(m, n, r, lo=-5 if r > 10 else -1, seed=m)
+    f, Q, R, I = O.pivoted_QR_of_specified_rank_or_prec(A, k, TOL)
+    f0, Q0, R0, I0 = ref32.pqr(A, k, TOL)
+    assert f == f0 and np.array_equal(I, I0)
+    assert np.linalg.norm(R - R0) <= 1e-11 * np.linalg.norm(R0) and np.linalg.norm(Q - Q0) <= 1e-11 * np.linalg.norm(Q0)
+
+
+def test_twin_deterministic_id_and_svd_match_reference(ref32):
+    A = _decaying(70, 90, 40, seed=5)
+    for k, TOL in [(15, 0.0), (0, 1e-4)]:
+        f, I, T = O.id_decomp_fixed_rank_or_prec(A, k, TOL)
+        f0, I0, T0 = ref32.id_decomp(A, k, TOL)
+        assert f == f0 and np.array_equal(I, I0) and np.linalg.norm(T - T0) <= 1e-9 * np.linalg.norm(T0)
+        f, Ic, Ir, T, S = O.id_two_sided_decomp_fixed_rank_or_prec(A, k, TOL)
+        f0, Ic0, Ir0, T0, S0 = ref32.id_two_sided_decomp(A, k, TOL)
+        assert f == f0 and np.array_equal(Ic, Ic0) and np.array_equal(Ir, Ir0) and np.linalg.norm(S - S0) <= 1e-9 * np.linalg.norm(S0)
+    for k, TOL in [(12, 0.0), (0, 3.0), (0, 0.5)]:
+        B = 7.5 * A
+        f, U, S, V = O.low_rank_svd_decomp_fixed_rank_or_prec(B, k, TOL)
+        f0, U0, S0, V0 = ref32.svd_decomp(B, k, TOL)
+        assert f == f0 and np.allclose(np.diag(S), np.diag(S0), rtol=1e-12)
+
+
+def test_twin_legacy_randqb_and_rank_estimate_match_reference(ref32):
+    A = _decaying(120, 90, 40, lo=-4, seed=9)
+    Q, B = O.randQB_p(A, 8, 1, seed=11)
+    Q0, B0 = ref32.randQB_p(A, 8, 1, seed=11)
+    assert np.linalg.norm(Q - Q0) < 1e-9 and np.linalg.norm(B - B0) < 1e-9
+    Q, B = O.randQB_pb(A, 6, 3, 1, 1, seed=5)
+    Q0, B0 = ref32.randQB_pb(A, 6, 3, 1, 1, seed=5)
+    assert np.linalg.norm(Q @ B - Q0 @ B0) <= 1e-10 * np.linalg.norm(A)
+    A = _decaying(100, 80, 12, lo=-2, seed=2)
+    r, Qe = O.estimate_rank_and_buildQ(A, 0.5, 1e-8, seed=3)
+    r0, Qe0 = ref32.estimate_rank1(A, 0.5, 1e-8, seed=3)
+    assert r == r0
+
+
+def test_twins_match_golden_baselines():
+    """tests/golden/golden_baselines.npz was produced by the compiled reference (tests/golden/make_golden.py); the numpy twins
+    must reproduce it without oracle/_ref being present."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_baselines.npz"))
+    A = g["A"]
+    f, Q, R, I = O.pivoted_QR_of_specified_rank_or_prec(A, 10, None)
+    assert f == int(g["pqr_k10_frank"]) and np.array_equal(I, g["pqr_k10_I"])
+    assert np.allclose(R, g["pqr_k10_R"], rtol=0, atol=1e-12) and np.allclose(Q, g["pqr_k10_Q"], rtol=0, atol=1e-12)
+    f, Q, R, I = O.pivoted_QR_of_specified_rank_or_prec(A, 0, 0.05)
+    assert f == int(g["pqr_tol_frank"]) and np.array_equal(I, g["pqr_tol_I"])
+    f, I, T = O.id_decomp_fixed_rank_or_prec(A, 12, 0.0)
+    assert f == int(g["id_k12_frank"]) and np.array_equal(I, g["id_k12_I"]) and np.allclose(T, g["id_k12_T"], atol=1e-10)
+    f, Ic, Ir, T, S = O.id_two_sided_decomp_fixed_rank_or_prec(A, 0, 0.05)
+    assert f == int(g["id2_tol_frank"]) and np.array_equal(Ic, g["id2_tol_Icol"]) and np.array_equal(Ir, g["id2_tol_Irow"])
+    assert np.allclose(np.diag(O.low_rank_svd_decomp_fixed_rank_or_prec(A, 7, 0.0)[2]), np.diag(g["svd_k7_S"]), rtol=1e-12)
+    assert O.low_rank_svd_decomp_fixed_rank_or_prec(A, 0, 2.0)[0] == int(g["svd_tol_frank"])
+    Q, B = O.randQB_p(A, 6, 1, seed=777)
+    assert np.allclose(Q, g["qbp_Q"], atol=1e-10) and np.allclose(B, g["qbp_B"], atol=1e-10)
+    Q, B = O.randQB_pb(A, 4, 3, 1, 1, seed=777)
+    assert np.allclose(Q @ B, g["qbpb_QB"], atol=1e-11)
+    assert O.estimate_rank_and_buildQ(A, 0.5, 1e-3, seed=777)[0] == int(g["rank1"])
