@@ -220,6 +220,8 @@ static int cholqr_pass(const double *Yin, i64 ldy, i64 m, i64 l, double *Qout, i
     DBuf G((size_t)l * l), Rinv((size_t)l * l), stat(2);
     Gemm g;   // Gram = Yin^T Yin
     g.ta = 'T'; g.tb = 'N'; g.m = l; g.n = l; g.k = m; g.A = Yin; g.lda = ldy; g.B = Yin; g.ldb = ldy; g.C = G.p; g.ldc = l;
+    g.sym_upper = true;                                   // potrf_upper reads the upper triangle only
+    set_zero(G.p, (size_t)l * l);                         // skipped tiles must not feed NaNs into the all-reduce / trailing updates
     gemm(g);
     if (sharded) allreduce_sum(G.p, (size_t)l * l);
     int info = potrf_upper(G.p, l, l);

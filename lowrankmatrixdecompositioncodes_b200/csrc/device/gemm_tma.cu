@@ -110,7 +110,13 @@ bool gemm_tma_try(const Gemm &g) {
     p.seed = g.seed; p.ph_sk = g.ph_sk; p.ph_sc = g.ph_sc; p.ph_off = g.ph_off;
     p.c_vec2 = (((uintptr_t)g.C & 15) == 0 && (g.ldc & 1) == 0) ? 1 : 0;
     const i64 tm = (g.m + BM - 1) / BM;
-    const i64 tiles = tm * T;
+    i64 tiles = tm * T;
+    p.sym = 0;
+    if (g.sym_upper && g.m == g.n && !g.philox) {           // only the tiles meeting the upper triangle
+        p.sym = 1;
+        tiles = 0;
+        for (i64 tn = 0; tn < T; ++tn) tiles += sym_rows((int)tm, 8 * nb_tile, (int)tn);
+    }
     if (tiles > 0x3fffffffll) return false;
     p.tiles_n = (int)T; p.nb_tile = nb_tile;
     p.total_iters = (int)((g.k + BK - 1) / BK);

@@ -25,8 +25,28 @@ struct TmaP {
     int main_tiles, s_main, s_tail;   // tiles [0,main_tiles) are split s_main ways, the rest s_tail ways
     double *part;         // partial tiles of split units
     int c_vec2;           // C rows can be stored as 16-byte pairs
+    int sym;              // C is symmetric and only its upper triangle is wanted: tiles entirely below the diagonal are skipped
     uint64_t seed; i64 ph_sk, ph_sc, ph_off;
 };
+
+// tile index -> (tile_m, tile_n).  Plain products: n-tiles vary fastest.  sym: only the tiles that meet the upper triangle,
+// enumerated column tile by column tile (tile_n holds rows 0 .. upper_rows(tile_n)-1).
+__host__ __device__ __forceinline__ int sym_rows(int tiles_m, int width, int tile_n) {   // row tiles meeting the upper triangle in column tile tile_n
+    const int last_col = width * tile_n + width - 1;
+    const int r = last_col / 128 + 1;          // BM = 128
+    return r < tiles_m ? r : tiles_m;
+}
+__device__ __forceinline__ void tile_to_mn(const TmaP &p, int tile, int &tile_m, int &tile_n) {
+    if (!p.sym) { tile_n = tile % p.tiles_n; tile_m = tile / p.tiles_n; return; }
+    const int tiles_m = (int)((p.m + 127) / 128), width = 8 * p.nb_tile;
+    int tn = 0;
+    for (;; ++tn) {
+        const int c = sym_rows(tiles_m, width, tn);
+        if (tile < c || tn == p.tiles_n - 1) break;
+        tile -= c;
+    }
+    tile_n = tn; tile_m = tile;
+}
 
 // ---- PTX helpers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,7 +117,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int warp = tid >> 5, lane = tid & 31;
     int tile, split, nsplit;
     decode_unit(p, (int)blockIdx.x, tile, split, nsplit);
-    const int tile_n = tile % p.tiles_n, tile_m = tile / p.tiles_n;
+    int tile_n, tile_m;
+    tile_to_mn(p, tile, tile_m, tile_n);
     const i64 m0 = (i64)tile_m * BM, n0 = (i64)tile_n * (8 * NB);
     // NB = column groups per n-tile (compile time).  Columns beyond n in the last tile are zero-filled by TMA (or
     // generated and never stored), so every tile runs the same branch-free inner loop.
@@ -338,7 +359,8 @@ static __global__ void __launch_bounds__(256) tile_reduce_kernel(TmaP p, int fir
     if (st < n_main_split) { tile = st; nsplit = p.s_main; unit0 = tile * p.s_main; }
     else { int tt = st - n_main_split; tile = p.main_tiles + tt; nsplit = p.s_tail; unit0 = p.main_tiles * p.s_main + tt * p.s_tail; }
     (void)first_split_tile_is_main;
-    const int tile_n = tile % p.tiles_n, tile_m = tile / p.tiles_n;
+    int tile_n, tile_m;
+    tile_to_mn(p, tile, tile_m, tile_n);
     const i64 m0 = (i64)tile_m * BM, n0 = (i64)tile_n * (8 * p.nb_tile);
     const int ncols = (int)min((i64)(8 * p.nb_tile), p.n - n0);
     const double *P = p.part + (i64)unit0 * PART_TILE;
