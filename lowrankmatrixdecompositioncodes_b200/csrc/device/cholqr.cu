@@ -236,6 +236,7 @@ static int cholqr_pass(const double *Yin, i64 ldy, i64 m, i64 l, double *Qout, i
     trtri_upper(G.p, l, l, Rinv.p, l);
     Gemm q;   // Qout = Yin * Rinv
     q.ta = 'N'; q.tb = 'N'; q.m = m; q.n = l; q.k = l; q.A = Yin; q.lda = ldy; q.B = Rinv.p; q.ldb = l; q.C = Qout; q.ldc = ldq;
+    q.b_upper = true;                                     // trtri_upper leaves exact zeros below the diagonal
     gemm(q);
     if (Rout) copy_matrix(G.p, l, Rout, l, l, l);
     return 0;

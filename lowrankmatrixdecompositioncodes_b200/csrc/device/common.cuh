@@ -86,6 +86,8 @@ struct Gemm {
     double *C = nullptr; i64 ldc = 0;
     int batch = 1; i64 sA = 0, sB = 0, sC = 0;   // strided batch
     bool philox = false; uint64_t seed = 0; i64 ph_sk = 0, ph_sc = 0, ph_off = 0;
+    bool b_upper = false;     // op(B) is upper triangular with exact zeros below the diagonal (hint: the streaming kernel stops each
+                              // column tile's contraction at the diagonal; other paths ignore it)
     bool sym_upper = false;   // C is symmetric (e.g. a Gram matrix) and only its upper triangle will be read: the streaming
                               // kernel may leave tiles entirely below the diagonal untouched (a hint; other paths ignore it)
 };

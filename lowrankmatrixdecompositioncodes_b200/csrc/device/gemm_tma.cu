@@ -111,6 +111,7 @@ bool gemm_tma_try(const Gemm &g) {
     p.c_vec2 = (((uintptr_t)g.C & 15) == 0 && (g.ldc & 1) == 0) ? 1 : 0;
     const i64 tm = (g.m + BM - 1) / BM;
     i64 tiles = tm * T;
+    p.b_upper = (g.b_upper && !g.philox) ? 1 : 0;
     p.sym = 0;
     if (g.sym_upper && g.m == g.n && !g.philox) {           // only the tiles meeting the upper triangle
         p.sym = 1;

@@ -26,6 +26,7 @@ struct TmaP {
     double *part;         // partial tiles of split units
     int c_vec2;           // C rows can be stored as 16-byte pairs
     int sym;              // C is symmetric and only its upper triangle is wanted: tiles entirely below the diagonal are skipped
+    int b_upper;          // op(B) (k x n) is upper triangular: column tile [n0, n0+w) only needs k < n0 + w
     uint64_t seed; i64 ph_sk, ph_sc, ph_off;
 };
 
@@ -122,9 +123,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const i64 m0 = (i64)tile_m * BM, n0 = (i64)tile_n * (8 * NB);
     // NB = column groups per n-tile (compile time).  Columns beyond n in the last tile are zero-filled by TMA (or
     // generated and never stored), so every tile runs the same branch-free inner loop.
-    const int ips = (p.total_iters + nsplit - 1) / nsplit;
+    const int titers = p.b_upper ? min(p.total_iters, (int)((n0 + 8 * NB + BK - 1) / BK)) : p.total_iters;   // rows of B below the diagonal are zero
+    const int ips = (titers + nsplit - 1) / nsplit;
     const int it0 = split * ips;
-    const int niter = max(0, min(p.total_iters, it0 + ips) - it0);
+    const int niter = max(0, min(titers, it0 + ips) - it0);
     constexpr uint32_t b_bytes = (uint32_t)(NB * 8 * BK * 8);
 
     if (tid == 0) {
