@@ -42,9 +42,11 @@ static int verbose(void) {
 }
 static uint64_t omega_seed(void) { return (uint64_t)rsvd_b200_get_option("seed"); }
 
+mat *rsvd_matrix_new_uninit(idx_t nrows, idx_t ncols);
 static mat *download_mat(const double *d, idx_t r, idx_t c) {
-    mat *M = matrix_new(r, c);
+    mat *M = d ? rsvd_matrix_new_uninit(r, c) : matrix_new(r, c);   /* fully overwritten by the download (zeros if there is nothing to download) */
     rsvd_download(M->d, d, (size_t)r * (size_t)c);
+    if (d && (g_api_status || rsvd_b200_status())) memset(M->d, 0, (size_t)r * (size_t)c * sizeof(double));   /* failed call: zeros, as documented */
     return M;
 }
 static vec *download_vec(const double *d, idx_t n) {

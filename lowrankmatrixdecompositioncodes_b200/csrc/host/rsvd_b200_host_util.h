@@ -8,5 +8,6 @@ void rsvd_api_begin(void);                     /* clear status at the start of a
 double *rsvd_upload(const double *h, size_t n);
 void rsvd_download(double *h, const double *d, size_t n);
 double *rsvd_host_calloc(size_t n);
+double *rsvd_host_alloc_uninit(size_t n);      /* like rsvd_host_calloc but a recycled pinned block is not cleared */
 void rsvd_host_free(double *p);
 #endif
