@@ -329,7 +329,20 @@ void orthonormalize(double *Y, i64 ldy, i64 m, i64 l, double *R, i64 ldr, bool s
             gemm(q2);
             accumulate_r(R3.p, R1.p, l);
             b2 = cholqr_pass(Q2.p, m, m, l, Y, ldy, R2.p, 1.0e12, sharded);
-            if (b2) { set_error("rsvd_b200: orthonormalisation failed (panel %lld x %lld is numerically singular)", (long long)m, (long long)l); return; }
+            if (b2) {
+                // Numerically rank-deficient panel (e.g. an exactly low-rank A sketched with more columns than its rank): no
+                // triangular solve can produce an orthonormal basis of all l columns.  Last resort = what the reference does
+                // (dgeqrf + dorgqr, MVF:1251-1263): Householder QR with the explicit Q, whose extra columns are an orthonormal
+                // completion.  BLAS-2 speed (one kernel per reflector), only ever reached on singular panels.
+                if (sharded && c.world > 1) {
+                    set_error("rsvd_b200: orthonormalisation failed (row-partitioned panel %lld x %lld is numerically singular)", (long long)m, (long long)l);
+                    return;
+                }
+                c.last_qr_path = 3;
+                geqrf_q(Y, ldy, m, l, R ? R1.p : nullptr, l);   // Y <- Q, R1 <- R
+                if (R) copy_matrix(R1.p, l, R, ldr, l, l);
+                return;
+            }
         }
     }
     if (R) {

@@ -47,7 +47,7 @@ struct Ctx {
     int force_generic_gemm = 0;
     int force_qr_fallback = 0;
     int jacobi_transpose = 0;        // run the one-sided Jacobi on R^T (lower triangular) instead of R
-    int last_qr_path = 0;            // 1 = CholeskyQR2, 2 = TSQR-preconditioned fallback
+    int last_qr_path = 0;            // 1 = CholeskyQR2, 2 = TSQR-preconditioned fallback, 3 = Householder with explicit Q (singular panel)
     unsigned long long qr_fallbacks = 0;
 };
 Ctx &ctx();
@@ -129,6 +129,8 @@ void trtri_upper(const double *R, i64 ldr, i64 n, double *Rinv, i64 ldi); // Rin
 void geqp3(double *A, i64 lda, i64 m, i64 n, double *jpvt_out);
 // unpivoted Householder, R only (upper triangle of A on exit), used by the TSQR fallback
 void geqrf_r(double *A, i64 lda, i64 m, i64 n);
+// dgeqrf + dorgqr (m >= n): A <- explicit thin Q (LAPACK sign convention), R (n x n upper, optional) — any rank
+void geqrf_q(double *A, i64 lda, i64 m, i64 n, double *R, i64 ldr);
 // the reference's own partial pivoted QR (RRA:1012-1334); returns frank
 i64 pqr_partial(double *A, i64 lda, i64 m, i64 n, i64 k, double tol, int zero_exact, double *I, double *Q, i64 ldq, double *R, i64 ldr);
 

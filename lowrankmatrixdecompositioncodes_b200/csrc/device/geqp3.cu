@@ -362,7 +362,9 @@ __global__ void int_to_double_kernel(const int *p, double *d, i64 n) {
 // the explicit factors Qout (m x frank) / Rout (frank x n), written for the first frank steps only.
 struct RefOpts { int tolmode; double tol; int zero_exact; i64 frank; double *Q; i64 ldq; double *R; i64 ldr; };
 
-void householder_qr(double *A, i64 lda, i64 m, i64 n, int pivoting, double *jpvt_out, i64 steps = -1, RefOpts *ro = nullptr) {
+// qr_out (pivoting == 0 only): after the factorisation A is replaced by the explicit thin Q and R (n x n upper) goes to Rq.
+void householder_qr(double *A, i64 lda, i64 m, i64 n, int pivoting, double *jpvt_out, i64 steps = -1, RefOpts *ro = nullptr,
+                    bool q_out = false, double *Rq = nullptr, i64 ldrq = 0) {
     if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     ensure_init();
     Ctx &c = ctx();
@@ -432,6 +434,21 @@ void householder_qr(double *A, i64 lda, i64 m, i64 n, int pivoting, double *jpvt
         }
         dfree(rc);
     }
+    if (q_out && pivoting == 0 && !g_status) {
+        const i64 f = steps;
+        if (Rq) {
+            extract_r_kernel<<<(int)min((i64)c.sms * 8, (f * n + 255) / 256), 256, 0, c.stream>>>(A, lda, f, n, Rq, ldrq);
+            count_launch();
+        }
+        DBuf Qb((size_t)m * f);
+        set_zero(Qb.p, (size_t)m * f);
+        set_identity(Qb.p, m, f);
+        for (i64 i = f - 1; i >= 0; --i) {
+            form_q_kernel<<<(int)(f - i), 256, 0, c.stream>>>(A, lda, m, i, tau.p, Qb.p, m);
+            count_launch();
+        }
+        copy_matrix(Qb.p, m, A, lda, m, f);
+    }
     RSVD_CUDA(cudaGetLastError());
     dfree(jpvt);
 }
@@ -440,6 +457,10 @@ void householder_qr(double *A, i64 lda, i64 m, i64 n, int pivoting, double *jpvt
 
 void geqp3(double *A, i64 lda, i64 m, i64 n, double *jpvt_out) { householder_qr(A, lda, m, n, 1, jpvt_out); }
 void geqrf_r(double *A, i64 lda, i64 m, i64 n) { householder_qr(A, lda, m, n, 0, nullptr); }
+void geqrf_q(double *A, i64 lda, i64 m, i64 n, double *R, i64 ldr) {
+    if (m < n) { set_error("rsvd_b200: explicit-Q Householder QR needs m >= n (got %lld x %lld)", (long long)m, (long long)n); return; }
+    householder_qr(A, lda, m, n, 0, nullptr, -1, nullptr, true, R, ldr);
+}
 
 // The reference's own partial pivoted QR (RRA:1012-1155 with zero_exact = 1, RRA:1159-1334 with zero_exact = 0).
 // k > 0: rank mode (at most k steps); k <= 0: tolerance mode (at most min(m,n) steps, stop when R22norm < tol).

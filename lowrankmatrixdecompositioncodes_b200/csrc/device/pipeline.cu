@@ -472,7 +472,7 @@ int svd_full(const double *A, i64 m, i64 n, i64 lda, double *U, i64 ldu, double 
     DBuf W((size_t)t * r), R((size_t)r * r), Uh((size_t)r * r), Vt((size_t)r * r);
     if (m >= n) copy_matrix(A, lda, W.p, t, m, n);
     else transpose(A, lda, W.p, t, m, n);                                  // W = A^T (n x m)
-    orthonormalize(W.p, t, t, r, R.p, r, /*sharded=*/false);               // W = Qw, R upper
+    orthonormalize(W.p, t, t, r, R.p, r, /*sharded=*/false);               // W = Qw, R upper (rank-deficient input: Householder completion)
     jacobi_svd(R.p, r, r, Uh.p, r, S, Vt.p, r);                            // R = Uh S Vt
     if (m >= n) {                                                          // A = (Qw Uh) S Vt
         mm('N', 'N', m, r, r, 1.0, W.p, t, Uh.p, r, 0.0, U, ldu);

@@ -315,3 +315,71 @@ def test_baselines_vs_committed_golden_vectors(api):
         assert np.max(np.abs(np.diag(S) - np.diag(g[name + "_S"]))) / np.diag(g[name + "_S"]).max() < tol, name
     assert api.estimate_rank1(A, 0.5, 1e-3, seed=777)[0] == int(g["rank1"])
     api.check()
+
+
+# ---- edge cases: the smallest shapes every new entry point accepts -----------------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (1, 5, 1), (5, 1, 1), (6, 9, 1), (9, 6, 6), (7, 7, 7)])
+def test_partial_pivoted_qr_edge_shapes(api, ref, m, n, k):
+    A = np.random.default_rng(10 * m + n).standard_normal((m, n)) + 0.1
+    f, Q, R, I = api.pqr(A, k, 0.0)
+    api.check()
+    f0, Q0, R0, I0 = ref.pqr(A, k, 0.0)
+    assert f == f0 and np.array_equal(I, I0)
+    assert relerr(R, R0) < 1e-10 and relerr(Q, Q0) < 1e-10
+    assert sorted(I.astype(int).tolist()) == list(range(n))
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (5, 1), (1, 5), (2, 2), (40, 3), (3, 40)])
+def test_full_svd_edge_shapes(api, m, n):
+    A = np.random.default_rng(m + 7 * n).standard_normal((m, n))
+    r = min(m, n)
+    f, U, S, V = api.svd_decomp(A, r, 0.0)
+    api.check()
+    assert f == r and relerr(U @ S @ V.T, A) < 1e-12
+    assert np.allclose(np.diag(S), np.linalg.svd(A, compute_uv=False), rtol=1e-12, atol=1e-14)
+
+
+def test_rank_deficient_inputs(api, ref):
+    u, v = np.arange(1.0, 31.0), np.cos(np.arange(20.0))
+    A = np.outer(u, v)                                                  # exactly rank 1
+    f, U, S, V = api.svd_decomp(A, 3, 0.0)
+    api.check()
+    assert abs(S[0, 0] - np.linalg.norm(u) * np.linalg.norm(v)) < 1e-10 * S[0, 0] and S[1, 1] < 1e-10 * S[0, 0]
+    f, Q, R, I = api.pqr(A, 5, 0.0)                                     # stops after one step: every remaining norm is ~0
+    f0, _, _, I0 = ref.pqr(A, 5, 0.0)
+    assert f == f0 == 1 and np.array_equal(I, I0)
+    f, I, T = api.id_decomp(A, 5, 0.0)
+    api.check()
+    assert f == 1 and T.shape == (1, 19) and relerr(A[:, I[:1].astype(int)] @ T, A[:, I[1:].astype(int)]) < 1e-12
+
+
+def test_legacy_entry_points_smallest_parameters(api, ref):
+    A = decaying(40, 30, 12, lo=-3, seed=1)
+    Q, B = api.randQB_p(A, 1, 0, seed=3)
+    Q0, B0 = ref.randQB_p(A, 1, 0, seed=3)
+    assert relerr(Q, Q0) < 1e-10 and relerr(B, B0) < 1e-10
+    Q, B = api.randQB_p(A, 2, 1, seed=3)                                # the Gram-Schmidt loop i < j-1 is still empty
+    Q0, B0 = ref.randQB_p(A, 2, 1, seed=3)
+    assert relerr(Q, Q0) < 1e-9 and relerr(B, B0) < 1e-9
+    Q, B = api.randQB_pb(A, 5, 1, 0, 1, seed=3)                         # one block, no power iteration
+    Q0, B0 = ref.randQB_pb(A, 5, 1, 0, 1, seed=3)
+    assert relerr(Q @ B, Q0 @ B0) < 1e-10
+    U, S, V = api.svd2(A, 1, seed=3)
+    assert S.shape == (1, 1) and abs(S[0, 0] - ref.svd2(A, 1, seed=3)[1][0, 0]) < 1e-10
+    r, Q = api.estimate_rank1(A, 1.0 / 30, 1e-8, seed=3)                # maxdim = 1
+    assert r == ref.estimate_rank1(A, 1.0 / 30, 1e-8, seed=3)[0] == 1 and Q.shape == (40, 1)
+    api.check()
+
+
+def test_invalid_parameters_are_reported_not_fatal(api):
+    A = decaying(20, 15, 8, seed=2)
+    for call in (lambda: api.pqr(A, 0), lambda: api.randQB_p(A, 0, 1), lambda: api.randQB_pb(A, 4, 0, 1, 1),
+                 lambda: api.randQB_pb(A, 10, 4, 1, 1), lambda: api.svd3(A, 4, 2, 0), lambda: api.estimate_rank1(A, 0.0, 1e-3),
+                 lambda: api.estimate_rank2(A, 0, 0.1)):
+        call()                                                           # returns (void API), outputs allocated
+        with pytest.raises(RuntimeError):
+            api.check()
+    f, Q, R, I = api.pqr(A, 99, 0.0)                                     # k > min(m,n): clamped, reported
+    assert f <= 15
+    with pytest.raises(RuntimeError):
+        api.check()

@@ -132,6 +132,23 @@ def test_orthonormalize(lib, m, l, cond, force):
         assert np.linalg.norm(Q - Qh @ (Qh.T @ Q)) < 1e-6
 
 
+@pytest.mark.parametrize("m,l,rank", [(3000, 64, 10), (500, 40, 1), (2000, 130, 129), (64, 8, 0)])
+def test_orthonormalize_exactly_rank_deficient_panel(lib, m, l, rank):
+    """A sketch with more columns than the matrix has rank (the reference's dgeqrf + dorgqr, MVF:1251-1263, returns an
+    orthonormal completion there): Q must be orthonormal, Q R = Y, R upper triangular — never an error."""
+    rng = np.random.default_rng(m + l)
+    Y = rng.standard_normal((m, rank)) @ rng.standard_normal((rank, l)) if rank else np.zeros((m, l))
+    Yd = D.from_numpy_cm(Y)
+    R = torch.zeros((l, l), dtype=torch.float64, device="cuda")
+    native.check(lib.rsvd_b200_orthonormalize(Yd.data_ptr(), m, m, l, R.data_ptr(), l))
+    sync(lib)
+    Q, Rn = D.to_numpy(Yd), R.t().cpu().numpy()
+    assert np.all(np.isfinite(Q)) and np.all(np.isfinite(Rn))
+    assert np.abs(Q.T @ Q - np.eye(l)).max() < 1e-12
+    assert np.linalg.norm(Q @ Rn - Y) <= 1e-12 * max(np.linalg.norm(Y), 1.0)
+    assert np.abs(np.tril(Rn, -1)).max() == 0.0
+
+
 @pytest.mark.parametrize("n", [1, 2, 5, 33, 120, 520, 1500])
 def test_jacobi_svd_and_eig(lib, n):
     rng = np.random.default_rng(n)
