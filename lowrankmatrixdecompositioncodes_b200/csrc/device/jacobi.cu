@@ -3,13 +3,14 @@
 // called at RRA:152 on the l x l factor Rhat) and compute_evals_and_evecs_of_symm_matrix (LAPACKE_dsyev,
 // MVF:1206-1209, called at RRA:190 on B*B^T).
 //
-// One sweep = N-1 round-robin steps of N/2 disjoint column pairs; each pair is one CTA that keeps both columns in
-// registers, forms the 2x2 Gram entries with a block reduction and rotates the columns of G and of the
-// accumulated V.  The l x l working set (<= 2 x 8.8 MB at l = 1050) stays L2-resident.
-// The whole iteration (all steps of all sweeps, convergence test included) is ONE persistent cooperative kernel: the
-// N/2 CTAs are co-resident and separate the steps with a device-wide barrier (an atomic counter in L2, ~1 us) instead
-// of one kernel launch per step (~4.3 us in a CUDA graph: 519 steps x 9 sweeps at l = 520).  A graph-replayed
-// per-step kernel remains as the fallback when the grid cannot be co-resident.
+// One sweep = N-1 steps of N/2 disjoint column pairs.  Columns are grouped in blocks of BW (2 by default); the blocks play a
+// round-robin tournament and a CTA keeps the 2*BW columns of two meeting blocks in registers for all their pairings, forming
+// the 2x2 Gram entries with block reductions and rotating the columns of G.  The rotations of V are only logged and replayed
+// afterwards (jacobi_replay_kernel).  The l x l working set (<= 2 x 8.8 MB at l = 1050) stays L2-resident.
+// The whole iteration (all rounds of all sweeps, convergence test included) is ONE persistent cooperative kernel: the CTAs are
+// co-resident and separate the rounds with a device-wide release/acquire barrier (an atomic counter in L2, ~1.3 us) instead of
+// one kernel launch per step (~4.3 us in a CUDA graph: 519 steps x 9 sweeps at l = 520).  A graph-replayed per-step kernel
+// (plain column pairs, V rotated in place, n <= 1280) remains as the fallback when a cooperative launch is not possible.
 #include "common.cuh"
 #include <algorithm>
 #include <vector>
