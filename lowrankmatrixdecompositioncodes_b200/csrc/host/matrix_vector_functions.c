@@ -179,6 +179,8 @@ double vector_get2norm(vec *v) {
     for (idx_t i = 0; i < v->nrows; ++i) s += v->d[i] * v->d[i];
     return sqrt(s);
 }
+/* MVF:314-340 stage every entry through an `int` (values are truncated before they are compared and returned); here the true
+ * minimum / maximum of the doubles is returned — identical for the integer-valued index vectors these helpers are used on. */
 void vector_get_min_element(vec *v, idx_t *minindex, double *minval) {
     idx_t bi = 0; double b = v->d[0];
     for (idx_t i = 1; i < v->nrows; ++i) if (v->d[i] < b) { b = v->d[i]; bi = i; }
@@ -238,8 +240,9 @@ double matrix_getmaxcolnorm(mat *M) {
     for (idx_t j = 0; j < M->ncols; ++j) { double s = sqrt(get_matrix_column_norm_squared(M, j)); if (s > b) b = s; }
     return b;
 }
+/* MVF:445-454: despite the name these are the SQUARED column norms (the reference's own pivoted QR downdates them as such) */
 void compute_matrix_column_norms(mat *M, vec *norms) {
-    for (idx_t j = 0; j < M->ncols; ++j) norms->d[j] = sqrt(get_matrix_column_norm_squared(M, j));
+    for (idx_t j = 0; j < M->ncols; ++j) norms->d[j] = get_matrix_column_norm_squared(M, j);
 }
 double get_percent_error_between_two_mats(mat *A, mat *B) {
     size_t N = (size_t)A->nrows * (size_t)A->ncols;
@@ -365,10 +368,11 @@ void fill_matrix_from_first_rows_from_list(mat *M, vec *I, idx_t k, mat *M_k) {
     for (idx_t j = 0; j < M->ncols; ++j)
         for (idx_t i = 0; i < k; ++i) EL(M_k, i, j) = EL(M, (idx_t)I->d[i], j);
 }
+/* MVF:1046-1060: the columns listed in I[k .. ncols-1] (ncols - k of them), i.e. everything AFTER the first k of the list */
 void fill_matrix_from_last_columns_from_list(mat *M, vec *I, idx_t k, mat *M_k) {
     idx_t n = M->ncols;
-    for (idx_t j = 0; j < k; ++j)
-        memcpy(&EL(M_k, 0, j), &EL(M, 0, (idx_t)I->d[n - k + j]), (size_t)M->nrows * sizeof(double));
+    for (idx_t j = k; j < n; ++j)
+        memcpy(&EL(M_k, 0, j - k), &EL(M, 0, (idx_t)I->d[j]), (size_t)M->nrows * sizeof(double));
 }
 static void resize_to(mat **M, idx_t r0, idx_t c0, idx_t nr, idx_t nc) {
     mat *R = matrix_new(nr, nc);
