@@ -73,6 +73,7 @@ void randQB_pb(mat *M, RSVD_INT kstep, RSVD_INT nstep, RSVD_INT p, RSVD_INT s, m
 /* ---- out-of-band status (the reference API is void and unchecked) ---- */
 int rsvd_b200_api_status(void);                 /* 0 = last call succeeded */
 const char *rsvd_b200_api_last_error(void);
+void rsvd_b200_api_clear_error(void);           /* reset the status (every rank_revealing_algorithms entry point does so on entry) */
 double rsvd_b200_api_last_percent_error(void);  /* value printed by the last use_*_for_approximation call */
 
 #ifdef __cplusplus

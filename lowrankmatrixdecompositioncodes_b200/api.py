@@ -79,8 +79,11 @@ class Api(_legacy_calls.LegacyCalls):
         native.dev().rsvd_b200_set_option(b"seed", int(seed))
 
     def check(self):
+        """Raise if the last API call reported an error (out-of-band: the reference API is void); reading clears the status."""
         if self.lib.rsvd_b200_api_status():
-            raise RuntimeError("rsvd_b200 api: " + self.lib.rsvd_b200_api_last_error().decode())
+            msg = self.lib.rsvd_b200_api_last_error().decode()
+            self.lib.rsvd_b200_api_clear_error()
+            raise RuntimeError("rsvd_b200 api: " + msg)
 
     def to_mat(self, a):
         a = np.asarray(a, dtype=np.float64)

@@ -32,6 +32,7 @@ void rsvd_api_begin(void) {
     rsvd_b200_clear_error();
 }
 int rsvd_b200_api_status(void) { rsvd_api_sync_error(); return g_api_status; }
+void rsvd_b200_api_clear_error(void) { rsvd_api_begin(); }   /* the helpers of matrix_vector_functions do not reset the status themselves */
 const char *rsvd_b200_api_last_error(void) { return g_api_err; }
 double rsvd_b200_api_last_percent_error(void) { return g_last_percent_error; }
 
