@@ -450,6 +450,47 @@ def estimate_rank_and_buildQ(M, frac_of_max_rank, TOL, seed=777):
     return good, QR_factorization_getQ(Qb[:, :good])
 
 
+def _cur_tail(M, Icol, Irow, T, k):
+    """RRA:2131-2177 / 2200-2252: C, U, R from a two-sided ID."""
+    n = M.shape[1]
+    Icolinv = np.empty(n, dtype=np.int64)
+    Icolinv[Icol.astype(np.int64)] = np.arange(n)
+    V = np.vstack([np.eye(k), T.T])[Icolinv, :]
+    R = M[Irow[:k].astype(np.int64), :]
+    Cm = M[:, Icol[:k].astype(np.int64)]
+    return Cm, square_matrix_system_solve(R @ R.T, R @ V).T, R
+
+
+def cur_decomp_fixed_rank_or_prec(M, k, TOL):
+    """RRA:2115-2187"""
+    frank, Icol, Irow, T, S = id_two_sided_decomp_fixed_rank_or_prec(M, k, TOL)
+    return (frank,) + _cur_tail(M, Icol, Irow, T, frank)
+
+
+def randomized_low_rank_svd1(M, k, seed=777):
+    """RRA:385-461 = the eig(B B^T) variant without oversampling or power iterations"""
+    return low_rank_svd_rand_decomp_fixed_rank(M, k, 0, 2, 1, 1, seed)
+
+
+def randomized_low_rank_svd2(M, k, seed=777):
+    """RRA:465-532"""
+    return low_rank_svd_rand_decomp_fixed_rank(M, k, 0, 1, 1, 1, seed)
+
+
+def randomized_low_rank_svd3(M, k, q, s, seed=777):
+    """RRA:536-634 (power loop j < q, the same orthonormalisation schedule as RRA:101-125)"""
+    return low_rank_svd_rand_decomp_fixed_rank(M, k, 0, 1, q, s, seed)
+
+
+def randomized_low_rank_svd4(M, kstep, nstep, p, seed=777):
+    """RRA:638-697: randQB_pb(M, kstep, nstep, p, 1), eig of B B^T, ascending singular values"""
+    Q, B = randQB_pb(M, kstep, nstep, p, 1, seed)
+    BBt = B @ B.T
+    evals, Uhat = compute_evals_and_evecs_of_symm_matrix(np.triu(BBt) + np.triu(BBt, 1).T)
+    sing = np.sqrt(evals)
+    return Q @ Uhat, np.diag(sing), B.T @ (Uhat @ np.diag(1.0 / sing))
+
+
 def make_matrix(m, n, spectrum="logspace", seed=0, k=None, tail=1e-8, rho=1.0 / 1.02):
     """make_matrix_binary.m:11-25 — A = U diag(sigma) V^T with Haar U, V.
     spectrum: 'logspace' (the reference's logspace(1,-3,p)), 'exp' (sigma_i = rho^i, the oneAPI

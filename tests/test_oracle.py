@@ -176,3 +176,17 @@ def test_twins_match_golden_baselines():
     Q, B = O.randQB_pb(A, 4, 3, 1, 1, seed=777)
     assert np.allclose(Q @ B, g["qbpb_QB"], atol=1e-11)
     assert O.estimate_rank_and_buildQ(A, 0.5, 1e-3, seed=777)[0] == int(g["rank1"])
+
+
+def test_legacy_svd_and_cur_twins_match_golden_baselines():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_baselines.npz"))
+    A = g["A"]
+    for name, args, tol in [("randomized_low_rank_svd1", (8,), 1e-7), ("randomized_low_rank_svd2", (8,), 1e-11),
+                            ("randomized_low_rank_svd3", (8, 3, 1), 1e-11), ("randomized_low_rank_svd4", (4, 2, 1), 1e-7)]:
+        S = getattr(O, name)(A, *args, seed=777)[1]
+        ref = np.diag(g[name.replace("randomized_low_rank_", "") + "_S"])
+        assert np.max(np.abs(np.diag(S) - ref)) / ref.max() < tol, name
+    f, Cm, U, R = O.cur_decomp_fixed_rank_or_prec(A, 9, 0.0)
+    assert np.array_equal(Cm, g["cur_k9_C"]) and np.array_equal(R, g["cur_k9_R"])
+    assert np.linalg.norm(Cm @ U @ R - g["cur_k9_C"] @ g["cur_k9_U"] @ g["cur_k9_R"]) <= 1e-9 * np.linalg.norm(A)
