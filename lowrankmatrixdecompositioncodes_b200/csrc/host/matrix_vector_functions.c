@@ -109,26 +109,43 @@ mat *matrix_load_from_binary_file(char *fname) {
         return NULL;
     }
     mat *M = matrix_new(m, n);
-    /* blocks of up to 32 MB of whole rows; each block is scattered into the column-major matrix by all cores, one cache line
-     * of the row-major block (8 columns of one row) at a time */
+    /* Blocks of up to 32 MB of whole rows, double-buffered: inside one parallel region a single thread reads block i+1 from
+     * the file while the others (and then that thread too: dynamic schedule) scatter block i into the column-major matrix, one
+     * cache line of the row-major block (8 columns of one row) at a time.  Page-cache reads (~4.6 GB/s) and the scatter
+     * (~4 GB/s on 8 cores) overlap instead of adding up. */
     size_t RB = n ? (((size_t)32 << 20) / ((size_t)n * sizeof(double))) : 1;
     if (RB < 8) RB = 8;
     if (RB > (size_t)(m ? m : 1)) RB = (size_t)(m ? m : 1);
-    double *buf = (double *)malloc(RB * (size_t)(n ? n : 1) * sizeof(double));
-    for (size_t i0 = 0; i0 < (size_t)m; i0 += RB) {
-        size_t rb = (size_t)m - i0 < RB ? (size_t)m - i0 : RB;
-        if (fread(buf, sizeof(double), rb * (size_t)n, fp) != rb * (size_t)n) {
-            rsvd_api_error("matrix_load_from_binary_file: %s is truncated", fname);
-            break;
+    const size_t bufn = RB * (size_t)(n ? n : 1);
+    double *bufs[2] = {(double *)malloc(bufn * sizeof(double)), (double *)malloc(bufn * sizeof(double))};
+    int truncated = 0;
+    size_t rb0 = (size_t)m < RB ? (size_t)m : RB;
+    if (m > 0 && n > 0 && fread(bufs[0], sizeof(double), rb0 * (size_t)n, fp) != rb0 * (size_t)n) truncated = 1;
+    int cur = 0;
+    for (size_t i0 = 0; i0 < (size_t)m && !truncated; i0 += RB, cur ^= 1) {
+        const size_t rb = (size_t)m - i0 < RB ? (size_t)m - i0 : RB;
+        const size_t i1 = i0 + RB;
+        const size_t rb_next = i1 < (size_t)m ? ((size_t)m - i1 < RB ? (size_t)m - i1 : RB) : 0;
+        const double *buf = bufs[cur];
+        double *next = bufs[cur ^ 1];
+        int bad = 0;
+        #pragma omp parallel
+        {
+            #pragma omp single nowait
+            {
+                if (rb_next && fread(next, sizeof(double), rb_next * (size_t)n, fp) != rb_next * (size_t)n) bad = 1;
+            }
+            #pragma omp for schedule(dynamic, 64)
+            for (long long j0 = 0; j0 < (long long)n; j0 += 8) {
+                size_t j1 = (size_t)j0 + 8 < (size_t)n ? (size_t)j0 + 8 : (size_t)n;
+                for (size_t r = 0; r < rb; ++r)
+                    for (size_t j = (size_t)j0; j < j1; ++j) M->d[j * (size_t)m + i0 + r] = buf[r * (size_t)n + j];
+            }
         }
-        #pragma omp parallel for schedule(static)
-        for (long long j0 = 0; j0 < (long long)n; j0 += 8) {
-            size_t j1 = (size_t)j0 + 8 < (size_t)n ? (size_t)j0 + 8 : (size_t)n;
-            for (size_t r = 0; r < rb; ++r)
-                for (size_t j = (size_t)j0; j < j1; ++j) M->d[j * (size_t)m + i0 + r] = buf[r * (size_t)n + j];
-        }
+        if (bad) truncated = 1;     /* the block just scattered was complete; the next one is not */
     }
-    free(buf);
+    if (truncated) rsvd_api_error("matrix_load_from_binary_file: %s is truncated", fname);
+    free(bufs[0]); free(bufs[1]);
     fclose(fp);
     return M;
 }
@@ -142,18 +159,35 @@ void matrix_write_to_binary_file(mat *M, char *fname) {
     size_t RB = n ? (((size_t)32 << 20) / ((size_t)n * sizeof(double))) : 1;
     if (RB < 8) RB = 8;
     if (RB > (size_t)(m ? m : 1)) RB = (size_t)(m ? m : 1);
-    double *buf = (double *)malloc(RB * (size_t)(n ? n : 1) * sizeof(double));
-    for (size_t i0 = 0; i0 < (size_t)m; i0 += RB) {
-        size_t rb = (size_t)m - i0 < RB ? (size_t)m - i0 : RB;
-        #pragma omp parallel for schedule(static)
-        for (long long j0 = 0; j0 < (long long)n; j0 += 8) {
-            size_t j1 = (size_t)j0 + 8 < (size_t)n ? (size_t)j0 + 8 : (size_t)n;
-            for (size_t r = 0; r < rb; ++r)
-                for (size_t j = (size_t)j0; j < j1; ++j) buf[r * (size_t)n + j] = M->d[j * (size_t)m + i0 + r];
+    /* double-buffered like the loader: one thread writes block i-1 while the others gather block i */
+    const size_t bufn = RB * (size_t)(n ? n : 1);
+    double *bufs[2] = {(double *)malloc(bufn * sizeof(double)), (double *)malloc(bufn * sizeof(double))};
+    int cur = 0, short_write = 0;
+    size_t pending = 0;                                      /* doubles of the previous block still to be written (in bufs[cur ^ 1]) */
+    for (size_t i0 = 0; i0 < (size_t)m || pending; i0 += RB, cur ^= 1) {
+        const size_t rb = i0 < (size_t)m ? ((size_t)m - i0 < RB ? (size_t)m - i0 : RB) : 0;
+        double *buf = bufs[cur];
+        const double *prev = bufs[cur ^ 1];
+        const size_t npend = pending;
+        int bad = 0;
+        #pragma omp parallel
+        {
+            #pragma omp single nowait
+            {
+                if (npend && fwrite(prev, sizeof(double), npend, fp) != npend) bad = 1;
+            }
+            #pragma omp for schedule(dynamic, 64)
+            for (long long j0 = 0; j0 < (long long)n; j0 += 8) {
+                size_t j1 = (size_t)j0 + 8 < (size_t)n ? (size_t)j0 + 8 : (size_t)n;
+                for (size_t r = 0; r < rb; ++r)
+                    for (size_t j = (size_t)j0; j < j1; ++j) buf[r * (size_t)n + j] = M->d[j * (size_t)m + i0 + r];
+            }
         }
-        fwrite(buf, sizeof(double), rb * (size_t)n, fp);
+        if (bad) { short_write = 1; break; }
+        pending = rb * (size_t)n;
     }
-    free(buf);
+    if (short_write) rsvd_api_error("matrix_write_to_binary_file: short write to %s", fname);
+    free(bufs[0]); free(bufs[1]);
     fclose(fp);
 }
 

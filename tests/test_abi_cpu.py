@@ -191,3 +191,29 @@ def test_jacobi_pair_schedule_is_a_complete_tournament(n, bw):
         assert len(set(pairs[st].ravel().tolist())) == N          # disjoint: all N columns appear once
     met = {(min(p, q), max(p, q)) for p, q in pairs.reshape(-1, 2).tolist()}
     assert len(met) == N * (N - 1) // 2 and all(p != q for p, q in met)
+
+
+def test_binary_loader_multi_block_and_truncated(tmp_path):
+    """The loader double-buffers 32 MB row blocks (>= 8 rows each): a wide matrix exercises several blocks and a ragged last
+    one; a truncated file is reported through the status channel and still returns a matrix (rows read so far)."""
+    api = pkg.Api(32)
+    m, n = 21, 524288 + 3                                     # 4 MB rows -> 8-row blocks: 8 + 8 + 5
+    A = np.random.default_rng(5).standard_normal((m, n))
+    f = str(tmp_path / "wide.bin")
+    O.write_matrix_binary(A, f, 32)
+    M = api.lib.matrix_load_from_binary_file(f.encode())
+    assert api.lib.rsvd_b200_api_status() == 0
+    assert np.array_equal(api.from_mat(M), A)
+    g = str(tmp_path / "wide_out.bin")
+    M = api.to_mat(A)
+    api.lib.matrix_write_to_binary_file(M, g.encode())
+    api.lib.matrix_delete(M)
+    assert open(f, "rb").read() == open(g, "rb").read()
+    data = open(f, "rb").read()
+    open(f, "wb").write(data[: 8 + 12 * n * 8 + 40])         # cut in the middle of the second block
+    api.lib.rsvd_b200_api_clear_error()
+    M = api.lib.matrix_load_from_binary_file(f.encode())
+    assert api.lib.rsvd_b200_api_status() != 0 and b"truncated" in api.lib.rsvd_b200_api_last_error()
+    B = api.from_mat(M)
+    assert B.shape == (m, n) and np.array_equal(B[:8], A[:8])
+    api.lib.rsvd_b200_api_clear_error()
