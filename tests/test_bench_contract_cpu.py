@@ -1,5 +1,6 @@
 """bench.py contract (reference arm, runs on the host cores — no GPU): exactly one JSON line on stdout carrying the keys the
-driver reads, with the reference's CPU path timed on a bounded sample of BASELINE configs[1]."""
+driver reads.  The default reference arm runs BASELINE configs[1] in full for every warm-up and timed step (about 20 s per call
+on the GPU box's host); the test passes --rows to keep the CPU suite short."""
 import json
 import os
 import subprocess
@@ -14,7 +15,7 @@ def test_reference_arm_prints_one_json_line():
     from oracle import ref_lib
     if not ref_lib.available(32):
         pytest.skip("compiled reference not present")
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--rows", "2500"],
                          capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
@@ -29,3 +30,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
     assert d["vs_baseline"] is None
+    assert d["steps"] == 2 and d["warmup"] == 1 and len(d["step_s"]) == 2          # honest counts: every call was made
+    assert d["config"]["rows_per_gpu"] == 2500 and d["config"]["global_shape"] == [2500, 20000]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.bench_config(1, 2500)                                # both arms print the same config object
