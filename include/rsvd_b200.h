@@ -35,7 +35,8 @@ void *rsvd_b200_stream(void);                   /* the cudaStream_t all kernels 
 void rsvd_b200_sync(void);
 unsigned long long rsvd_b200_launch_count(void); /* kernels launched by this library so far */
 /* options: "seed" (Omega seed, default 777 = the reference's unused `#define SEED 777`, MVH:10),
- * "verbose", "force_generic_gemm", "force_qr_fallback" */
+ * "verbose", "force_generic_gemm", "force_qr_fallback", "single_device" (host-level calls ignore the worker pool);
+ * in a process-per-GPU job "row0" / "m_global" place this rank's row block in the global matrix */
 void rsvd_b200_set_option(const char *name, rsvd_i64 value);
 rsvd_i64 rsvd_b200_get_option(const char *name); /* also "last_gemm_path", "last_qr_path", "qr_fallbacks", "sms" */
 
@@ -164,6 +165,46 @@ int rsvd_b200_pqr_partial_dev(double *Awork, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 
  * MVF:391-405,1304-1318) without forming the dense m x n product at once. */
 double rsvd_b200_svd_percent_error_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, const double *U, rsvd_i64 ldu,
                                        const double *S, const double *V, rsvd_i64 ldv, rsvd_i64 k);
+
+/* ---- host-level entry points: HOST matrix in, HOST factors out (hostapi.cu) -----------------------------------------------
+ * What the C host code calls for the reference API functions of the hot path.  h_A is column-major m x n with leading
+ * dimension ldh (pinned memory uploads at PCIe speed; pageable memory works).  The upload is pipelined in column chunks with
+ * the first pass of the algorithm.  With several active devices (RSVD_B200_DEVICES / rsvd_b200_set_devices) the matrix is
+ * row-partitioned over them inside the call; otherwise the call runs on the calling thread's device (and, in a
+ * process-per-GPU job set up with rsvd_b200_comm_init, h_A is this rank's row block). */
+int rsvd_b200_svd_rand_h(const double *h_A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 ldh, rsvd_i64 k, rsvd_i64 p, int vnum, int q, int s,
+                         uint64_t seed, double *h_U, rsvd_i64 ldu, double *h_S, double *h_V, rsvd_i64 ldv);   /* RRA:73-234 */
+int rsvd_b200_id_rand_h(const double *h_A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 ldh, rsvd_i64 k, rsvd_i64 p, int q, int s, uint64_t seed,
+                        double *h_I, double *h_T, rsvd_i64 ldt);                                              /* RRA:1863-1965 */
+int rsvd_b200_id_two_sided_rand_h(const double *h_A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 ldh, rsvd_i64 k, rsvd_i64 p, int q, int s, uint64_t seed,
+                                  double *h_Icol, double *h_Irow, double *h_T, rsvd_i64 ldt, double *h_S, rsvd_i64 lds);   /* RRA:2060-2082 */
+int rsvd_b200_cur_rand_h(const double *h_A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 ldh, rsvd_i64 k, rsvd_i64 p, int q, int s, uint64_t seed,
+                         double *h_C, rsvd_i64 ldc, double *h_U, rsvd_i64 ldu, double *h_R, rsvd_i64 ldr);   /* RRA:2191-2258 */
+/* randQB_pb_new (RRA:1576-1801): Q (m x cap), B (cap x n) and the residual M - QB stay in HBM behind the returned handle
+ * (NULL on failure); *frank = columns produced (nstep <= 0: tolerance mode, evaluated on the device). */
+void *rsvd_b200_randqb_h(const double *h_A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 ldh, rsvd_i64 kstep, rsvd_i64 nstep, rsvd_i64 cap, double tol,
+                         int q, int s, uint64_t seed, rsvd_i64 *frank);
+rsvd_i64 rsvd_b200_qb_parts(void *qb);                     /* devices the result is partitioned over */
+int rsvd_b200_qb_download(void *qb, rsvd_i64 cols, double *h_Q, rsvd_i64 ldq, double *h_B, rsvd_i64 ldb);
+/* SVD tail of low_rank_svd_blockrand_decomp_fixed_rank_or_prec (RRA:289-380) from the QB result alone: M^T Q is rebuilt as
+ * Ares^T Q + B^T (Q^T Q), so the original M is not uploaded again.  l = rows of B used, kk = rank kept. */
+int rsvd_b200_qb_svd(void *qb, rsvd_i64 l, rsvd_i64 kk, int vnum, double *h_U, rsvd_i64 ldu, double *h_S, double *h_V, rsvd_i64 ldv);
+int rsvd_b200_qb_dev_ptrs(void *qb, double **dAres, double **dQ, double **dB);   /* single-device results only */
+void rsvd_b200_qb_release_handle(void *qb);   /* after rsvd_b200_qb_dev_ptrs: the three buffers now belong to the caller (rsvd_b200_dev_free) */
+void rsvd_b200_qb_free(void *qb);
+/* residency across calls: after rsvd_b200_pin_matrix(h_A, m, n) the first host-level call that uploads h_A keeps the device
+ * copy, later calls on the same pointer skip the upload (the caller promises not to modify h_A meanwhile);
+ * rsvd_b200_unpin_matrix releases it.  Reference drivers call several routines on one M (driver_multi_core_mkl3.c:51,82,92,112). */
+int rsvd_b200_pin_matrix(const double *h_A, rsvd_i64 m, rsvd_i64 n);
+void rsvd_b200_unpin_matrix(const double *h_A);
+int rsvd_b200_is_resident(const double *h_A);
+
+/* ---- single-process multi-GPU (multi.cu): one worker thread and one NCCL rank per device inside this process ---------------
+ * The reference's caller is one single-threaded C process (multi_core_mkl_code_64bit/driver1.c:40-50); with
+ * RSVD_B200_DEVICES=0-7 (or "all", "0,2,5") in the environment — or this call — the host-level entry points above use all
+ * listed GPUs for one API call.  n <= 1 returns to single-device operation. */
+int rsvd_b200_set_devices(int n, const int *ids);
+int rsvd_b200_active_devices(void);
 
 /* ---- row-partitioned multi-GPU (one process per GPU; A_g = rows of this rank) ------------------------- */
 /* NCCL is used only for the sums of n x l products and l x l Gram matrices. */

@@ -97,8 +97,7 @@ int potrf_upper(double *G, i64 ldg, i64 n) {
     RSVD_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx().stream));
     DBuf W((size_t)PB * PB), T((size_t)PB * (n > PB ? n - PB : 1));
     const size_t potf2_bytes = (2 * PB * (PB + 1) + 2 * PB + 2) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) { RSVD_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potf2_bytes)); attr_set = true; }
+    RSVD_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potf2_bytes));   // per device: cheap enough per call
     for (i64 j0 = 0; j0 < n; j0 += PB) {
         int jb = (int)min((i64)PB, n - j0);
         potf2_inv_kernel<<<1, PB * PT, potf2_bytes, ctx().stream>>>(G, ldg, j0, jb, W.p, flag);

@@ -18,6 +18,7 @@ typedef long long i64;
 // ---- error channel (the reference API is `void`; errors are reported out of band) -------------
 void set_error(const char *fmt, ...);
 extern int g_status;
+extern int g_single_device;              // option "single_device": host-level calls ignore the worker pool (tails that need all of M on one GPU)
 
 #define RSVD_CUDA(call)                                                                      \
     do {                                                                                     \
@@ -47,16 +48,20 @@ struct Ctx {
     int force_generic_gemm = 0;
     int force_qr_fallback = 0;
     int jacobi_transpose = 0;        // run the one-sided Jacobi on R^T (lower triangular) instead of R
+    void *staging = nullptr;         // pinned staging buffers of this context (runtime.cu)
     int last_qr_path = 0;            // 1 = CholeskyQR2, 2 = TSQR-preconditioned fallback, 3 = Householder with explicit Q (singular panel)
     unsigned long long qr_fallbacks = 0;
 };
-Ctx &ctx();
+Ctx &ctx();                          // the calling thread's context (primary context unless a worker bound its own)
+void bind_ctx(Ctx *c);               // multi.cu: worker threads bind one context per device
+int init_ctx(Ctx &c, int device);
 void ensure_init();
 
 double *dalloc(size_t n_doubles);
 void *dalloc_bytes(size_t bytes);
 void dfree(void *p);
-inline void count_launch(int n = 1) { ctx().launches += (unsigned long long)n; }
+extern unsigned long long g_launches;            // all contexts together (approximate under concurrent workers: statistics only)
+inline void count_launch(int n = 1) { ctx().launches += (unsigned long long)n; __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 // RAII device buffer
 struct DBuf {
@@ -74,6 +79,20 @@ struct DBuf {
     operator double *() const { return p; }
 };
 
+// ---- pipelined upload (hostapi.cu) ---------------------------------------------------------------
+// A host matrix arriving in column chunks on the copy stream: ev[i] fires when columns [i*cw, (i+1)*cw) are in HBM.
+// An empty event list means "already resident".  The first pass of every algorithm consumes the chunks as they land.
+}  // namespace rsvd
+#include <vector>
+namespace rsvd {
+struct Upload {
+    i64 cw = 0;
+    std::vector<cudaEvent_t> ev;
+};
+// h: host matrix block (rows x n, leading dimension ldh doubles) -> dA (rows x n, ld rows) on the calling context's copy stream
+void upload_begin(const double *h, i64 ldh, double *dA, i64 rows, i64 n, Upload &up);
+void upload_end(Upload &up);
+
 // ---- GEMM engine (gemm.cu) ---------------------------------------------------------------------
 // C(m x n) = alpha * op(A)(m x k) * op(B)(k x n) + beta * C, column-major everywhere.
 // If `philox` is set, op(B)(kk, j) is not read from memory: it is normal(seed, ph_off + kk*ph_sk + j*ph_sc).
@@ -88,6 +107,8 @@ struct Gemm {
     bool philox = false; uint64_t seed = 0; i64 ph_sk = 0, ph_sc = 0, ph_off = 0;
     bool b_upper = false;     // op(B) is upper triangular with exact zeros below the diagonal (hint: the streaming kernel stops each
                               // column tile's contraction at the diagonal; other paths ignore it)
+    double *sumsq_out = nullptr;   // non-null: also return sum(C .^ 2) of the updated C (device scalar), fused into the streaming
+                                   // kernel's epilogue when it serves the call, a separate pass otherwise
     bool sym_upper = false;   // C is symmetric (e.g. a Gram matrix) and only its upper triangle will be read: the streaming
                               // kernel may leave tiles entirely below the diagonal untouched (a hint; other paths ignore it)
 };
@@ -107,6 +128,7 @@ void gather_rows(const double *A, i64 lda, i64 n, const double *idx, i64 k, doub
 void scale_cols(double *A, i64 lda, i64 m, i64 n, const double *s, int invert);
 double frob_norm(const double *A, i64 lda, i64 m, i64 n);                     // syncs
 void sumsq_async(const double *A, i64 lda, i64 m, i64 n, double *d_out);      // d_out[0] = sum of squares
+void sum_array_async(const double *part, i64 n, double *d_out);               // d_out[0] = sum(part[0:n]) in a fixed order
 void fill_normal(double *A, i64 n_entries, uint64_t seed, i64 first);
 void trsm_left_upper(const double *R, i64 ldr, i64 k, double *B, i64 ldb, i64 ncols);  // B <- R^{-1} B
 int lu_solve(double *A, i64 lda, i64 n, double *B, i64 ldb, i64 nrhs);        // dgesv semantics, in place
@@ -142,5 +164,16 @@ void jacobi_eig(double *A, i64 lda, i64 n, double *w);
 
 // ---- collectives (dist.cu) ---------------------------------------------------------------------
 void allreduce_sum(double *d, size_t count);      // no-op when world == 1
+void allgather(const double *send, double *recv, size_t count);   // recv = [rank 0's count doubles | rank 1's | ...]
+int nccl_unique_id(char id_out[128]);
+int nccl_join(int rank, int world, const char id[128]);            // the calling thread's context joins a communicator
+void nccl_leave();
+
+// ---- single-process multi-GPU (multi.cu): one worker thread + context per device ----------------
+int pool_size();                                  // devices driven by this process (1 = the calling thread's context only)
+}  // namespace rsvd
+#include <functional>
+namespace rsvd {
+void pool_run(const std::function<void(int)> &fn);   // fn(rank) on every worker (inline when pool_size() == 1); blocks
 
 }  // namespace rsvd

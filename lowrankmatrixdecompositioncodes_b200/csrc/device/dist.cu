@@ -6,6 +6,7 @@
 // framework may already have loaded.
 #include "common.cuh"
 #include <dlfcn.h>
+#include <mutex>
 
 namespace rsvd {
 
@@ -14,6 +15,7 @@ typedef struct { char internal[128]; } NcclUniqueId;
 typedef int (*GetUniqueIdFn)(NcclUniqueId *);
 typedef int (*CommInitRankFn)(void **, int, NcclUniqueId, int);
 typedef int (*AllReduceFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*AllGatherFn)(const void *, void *, size_t, int, void *, cudaStream_t);
 typedef int (*CommDestroyFn)(void *);
 typedef const char *(*GetErrorStringFn)(int);
 
@@ -22,9 +24,12 @@ struct Nccl {
     GetUniqueIdFn get_unique_id = nullptr;
     CommInitRankFn comm_init_rank = nullptr;
     AllReduceFn all_reduce = nullptr;
+    AllGatherFn all_gather = nullptr;
     CommDestroyFn comm_destroy = nullptr;
     GetErrorStringFn error_string = nullptr;
+    std::mutex mu;
     bool load() {
+        std::lock_guard<std::mutex> lk(mu);
         if (h) return true;
         h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
         if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -33,9 +38,10 @@ struct Nccl {
         get_unique_id = (GetUniqueIdFn)dlsym(h, "ncclGetUniqueId");
         comm_init_rank = (CommInitRankFn)dlsym(h, "ncclCommInitRank");
         all_reduce = (AllReduceFn)dlsym(h, "ncclAllReduce");
+        all_gather = (AllGatherFn)dlsym(h, "ncclAllGather");
         comm_destroy = (CommDestroyFn)dlsym(h, "ncclCommDestroy");
         error_string = (GetErrorStringFn)dlsym(h, "ncclGetErrorString");
-        if (!get_unique_id || !comm_init_rank || !all_reduce || !comm_destroy) {
+        if (!get_unique_id || !comm_init_rank || !all_reduce || !all_gather || !comm_destroy) {
             set_error("rsvd_b200: libnccl is missing required symbols");
             return false;
         }
@@ -54,13 +60,20 @@ void allreduce_sum(double *d, size_t count) {
     if (r != 0) set_error("rsvd_b200: ncclAllReduce failed: %s", g_nccl.error_string ? g_nccl.error_string(r) : "?");
 }
 
-}  // namespace rsvd
+// recv (world * count doubles) = concatenation over ranks of each rank's `count` doubles at send.  world == 1: a copy.
+void allgather(const double *send, double *recv, size_t count) {
+    Ctx &c = ctx();
+    if (count == 0) return;
+    if (c.world <= 1) {
+        if (send != recv) RSVD_CUDA(cudaMemcpyAsync(recv, send, count * 8, cudaMemcpyDeviceToDevice, c.stream));
+        return;
+    }
+    if (!c.nccl_comm) { set_error("rsvd_b200: world=%d but no communicator", c.world); return; }
+    int r = g_nccl.all_gather(send, recv, count, kNcclFloat64, c.nccl_comm, c.stream);
+    if (r != 0) set_error("rsvd_b200: ncclAllGather failed: %s", g_nccl.error_string ? g_nccl.error_string(r) : "?");
+}
 
-using namespace rsvd;
-
-extern "C" {
-
-int rsvd_b200_comm_unique_id(char id_out[128]) {
+int nccl_unique_id(char id_out[128]) {
     if (!g_nccl.load()) return 1;
     NcclUniqueId id;
     int r = g_nccl.get_unique_id(&id);
@@ -69,10 +82,9 @@ int rsvd_b200_comm_unique_id(char id_out[128]) {
     return 0;
 }
 
-int rsvd_b200_comm_init(int rank, int world, const char id_in[128]) {
-    ensure_init();
+// joins the calling thread's context (already initialised on its device) to a communicator of `world` ranks
+int nccl_join(int rank, int world, const char id_in[128]) {
     Ctx &c = ctx();
-    if (!c.inited) return 1;
     if (world <= 1) { c.rank = 0; c.world = 1; return 0; }
     if (!g_nccl.load()) return 1;
     NcclUniqueId id;
@@ -84,11 +96,27 @@ int rsvd_b200_comm_init(int rank, int world, const char id_in[128]) {
     return 0;
 }
 
-void rsvd_b200_comm_destroy(void) {
+void nccl_leave() {
     Ctx &c = ctx();
     if (c.nccl_comm) { cudaStreamSynchronize(c.stream); g_nccl.comm_destroy(c.nccl_comm); }
     c.nccl_comm = nullptr; c.rank = 0; c.world = 1;
 }
+
+}  // namespace rsvd
+
+using namespace rsvd;
+
+extern "C" {
+
+int rsvd_b200_comm_unique_id(char id_out[128]) { return nccl_unique_id(id_out); }
+
+int rsvd_b200_comm_init(int rank, int world, const char id_in[128]) {
+    ensure_init();
+    if (!ctx().inited) return 1;
+    return nccl_join(rank, world, id_in);
+}
+
+void rsvd_b200_comm_destroy(void) { nccl_leave(); }
 
 int rsvd_b200_allreduce_sum(double *d, rsvd_i64 count) { allreduce_sum(d, (size_t)count); return g_status; }
 

@@ -201,6 +201,7 @@ void gemm(const Gemm &g) {
     if (!ctx().force_generic_gemm && gemm_tma_try(g)) { g_last_gemm_path = 1; return; }
     g_last_gemm_path = 0;
     gemm_generic(g);
+    if (g.sumsq_out) sumsq_async(g.C, g.ldc, g.m, g.n, g.sumsq_out);   // the generic kernel has no fused norm: separate pass
 }
 
 // ---- FP64 peak micro-benchmark -----------------------------------------------------------------------

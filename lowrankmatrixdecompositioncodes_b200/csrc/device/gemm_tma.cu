@@ -122,7 +122,8 @@ bool gemm_tma_try(const Gemm &g) {
     p.tiles_n = (int)T; p.nb_tile = nb_tile;
     p.total_iters = (int)((g.k + BK - 1) / BK);
     const int sms = ctx().sms;
-    const int max_split = max(1, min(16, p.total_iters / 32));   // keep >= 32 k-iterations per unit
+    int max_split = max(1, min(16, p.total_iters / 32));   // keep >= 32 k-iterations per unit
+    if (g.sumsq_out) max_split = 1;                        // the fused norm lives in the direct-store epilogue
     p.main_tiles = (int)tiles; p.s_main = 1; p.s_tail = 1;
     if (tiles < sms) {
         // under-filled: split every tile so that ~all SMs are busy
@@ -148,6 +149,9 @@ bool gemm_tma_try(const Gemm &g) {
         part.alloc((size_t)(units - first_split_unit) * PART_TILE);
         p.part = part.p - first_split_unit * PART_TILE;
     }
+    DBuf ss_part;
+    p.ss_part = nullptr;
+    if (g.sumsq_out) { ss_part.alloc((size_t)units * 8); p.ss_part = ss_part.p; }
     bool launched = false;
     switch (nb_tile) {
         case 4: launched = launch_tma<4>(ta, g.philox, mapA, mapB, p, (unsigned)units); break;
@@ -165,6 +169,7 @@ bool gemm_tma_try(const Gemm &g) {
         tile_reduce_kernel<<<(unsigned)split_tiles, 256, 0, ctx().stream>>>(p, 0);
         count_launch();
     }
+    if (g.sumsq_out) sum_array_async(ss_part.p, units * 8, g.sumsq_out);
     return cudaGetLastError() == cudaSuccess;
 }
 

@@ -28,6 +28,7 @@ struct TmaP {
     int sym;              // C is symmetric and only its upper triangle is wanted: tiles entirely below the diagonal are skipped
     int b_upper;          // op(B) (k x n) is upper triangular: column tile [n0, n0+w) only needs k < n0 + w
     uint64_t seed; i64 ph_sk, ph_sc, ph_off;
+    double *ss_part;      // non-null: consumer warp w of unit u also writes the sum of squares of the C entries it stored to ss_part[8u + w]
 };
 
 // tile index -> (tile_m, tile_n).  Plain products: n-tiles vary fastest.  sym: only the tiles that meet the upper triangle,
@@ -314,6 +315,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     }
         } else {
             const double alpha = p.alpha, beta = p.beta;
+            double ss = 0.0;          // fused Frobenius norm of the updated C (randQB_pb_new: ||A - Qp Bp||_F, RRA:1750-1751,1771)
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
@@ -329,6 +331,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                     double v = alpha * acc[x][nb][cc];
                                     if (beta != 0.0) v += beta * cp[row];
                                     cp[row] = v;
+                                    ss = fma(v, v, ss);
                                 }
                             }
                         } else {
@@ -338,6 +341,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                 double2 *dst = reinterpret_cast<double2 *>(cp + row);
                                 if (beta != 0.0) { double2 o = *dst; v.x += beta * o.x; v.y += beta * o.y; }
                                 *dst = v;
+                                ss = fma(v.x, v.x, fma(v.y, v.y, ss));
                             } else {
 #pragma unroll
                                 for (int x = 0; x < 2; ++x)
@@ -345,10 +349,16 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                         double v = alpha * acc[x][nb][cc];
                                         if (beta != 0.0) v += beta * cp[row + x];
                                         cp[row + x] = v;
+                                        ss = fma(v, v, ss);
                                     }
                             }
                         }
                     }
+            if (p.ss_part) {          // fixed-order reduction: shuffle tree per warp, one slot per (unit, warp); summed by a second kernel
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                if (lane == 0) p.ss_part[(i64)blockIdx.x * 8 + cw] = ss;
+            }
         }
     }
 }

@@ -5,7 +5,7 @@
 //
 // Row partition (world > 1): `A` is this rank's block of rows; m is the local row count.  Products that contract
 // over rows (A^T * X) are all-reduced; n x l panels are replicated, m x l panels are row-sharded.
-#include "common.cuh"
+#include "pipeline.cuh"
 #include <vector>
 
 namespace rsvd {
@@ -105,14 +105,36 @@ __global__ void tol_check_kernel(const double *sumsq, double tol, int *done, dou
 // ---------------------------------------------------------------------------------------------------------
 // SVD tail (RRA:133-225 and RRA:289-380)
 // ---------------------------------------------------------------------------------------------------------
+// factors from Bt = A^T Q (n x l, replicated; destroyed) and the orthonormal Q (m x l, row-sharded)
+static int svd_tail(DBuf &Bt, i64 m, i64 n, double *Q, i64 ldq, i64 l, i64 k, int vnum, double *U, i64 ldu, double *S, double *V, i64 ldv, Phase &ph);
+
 int svd_from_q(const double *A, i64 m, i64 n, i64 lda, double *Q, i64 ldq, i64 l, i64 k, int vnum,
                double *U, i64 ldu, double *S, double *V, i64 ldv) {
-    Ctx &c = ctx();
     DBuf Bt((size_t)n * l);
     Phase ph;
     mm('T', 'N', n, l, m, 1.0, A, lda, Q, ldq, 0.0, Bt.p, n);          // Bt = A^T Q   (RRA:139)  — last pass over A
     allreduce_sum(Bt.p, (size_t)n * l);
     ph.lap("Bt = A^T Q");
+    return svd_tail(Bt, m, n, Q, ldq, l, k, vnum, U, ldu, S, V, ldv, ph);
+}
+
+// The same tail when only the QB RESIDUAL Ares = M - Q B is in HBM (randQB_pb_new overwrites its private copy, RRA:1750):
+// M^T Q = Ares^T Q + B^T (Q^T Q), exact algebra — one pass over the residual (the pass the tail makes anyway), an l x l Gram
+// matrix and an n x l x l product instead of re-uploading M from the host (80 GB at BASELINE configs[2]).
+int svd_from_q_residual(const double *Ares, i64 m, i64 n, i64 lda, double *Q, i64 ldq, i64 l, const double *B, i64 ldb, i64 k, int vnum,
+                        double *U, i64 ldu, double *S, double *V, i64 ldv) {
+    DBuf Bt((size_t)n * l), G((size_t)l * l);
+    Phase ph;
+    mm('T', 'N', n, l, m, 1.0, Ares, lda, Q, ldq, 0.0, Bt.p, n);
+    mm('T', 'N', l, l, m, 1.0, Q, ldq, Q, ldq, 0.0, G.p, l);
+    if (ctx().world > 1) { allreduce_sum(Bt.p, (size_t)n * l); allreduce_sum(G.p, (size_t)l * l); }
+    mm('T', 'N', n, l, l, 1.0, B, ldb, G.p, l, 1.0, Bt.p, n);          // Bt += B^T (Q^T Q)
+    ph.lap("Bt = Ares^T Q + B^T QtQ");
+    return svd_tail(Bt, m, n, Q, ldq, l, k, vnum, U, ldu, S, V, ldv, ph);
+}
+
+static int svd_tail(DBuf &Bt, i64 m, i64 n, double *Q, i64 ldq, i64 l, i64 k, int vnum, double *U, i64 ldu, double *S, double *V, i64 ldv, Phase &ph) {
+    Ctx &c = ctx();
     if (vnum == 1 || vnum > 2) {
         DBuf Rhat((size_t)l * l), Uhat((size_t)l * l), Vhat_t((size_t)l * l), Vhat((size_t)l * l), sv((size_t)l);
         orthonormalize(Bt.p, n, n, l, Rhat.p, l, /*sharded=*/false);      // [Qhat, Rhat] = qr(Bt)  (RRA:146); Qhat overwrites Bt
@@ -152,9 +174,26 @@ int svd_from_q(const double *A, i64 m, i64 n, i64 lda, double *Q, i64 ldq, i64 l
 // ---------------------------------------------------------------------------------------------------------
 // low_rank_svd_rand_decomp_fixed_rank (RRA:73-234)
 // ---------------------------------------------------------------------------------------------------------
-// `Y0` (optional): an already computed sketch A*Omega (m x l, ld m) — used when the upload of A was pipelined with it.
-static int svd_rand_impl(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int vnum, int q, int s, uint64_t seed,
-                         const double *omega, DBuf *Y0, double *U, i64 ldu, double *S, double *V, i64 ldv) {
+// Y = A * Omega(:, block) for a matrix that may still be arriving: with `up` the sketch consumes the column chunks of A
+// as their upload events fire (Y += A(:,chunk) * Omega(chunk,:), Omega generated in the kernel), so the first pass over A
+// hides behind the PCIe transfer.  Omega(kk, j) = normal(seed, off + kk + j*n).
+static void sketch_chunked(const double *A, i64 m, i64 n, i64 lda, i64 l, uint64_t seed, i64 off, double *Y, i64 ldy, const Upload *up) {
+    Ctx &c = ctx();
+    if (!up || up->ev.empty()) { sketch('N', m, l, n, A, lda, seed, 1, n, off, Y, ldy); return; }
+    for (size_t i = 0; i < up->ev.size(); ++i) {
+        const i64 c0 = (i64)i * up->cw, w = std::min(up->cw, n - c0);
+        RSVD_CUDA(cudaStreamWaitEvent(c.stream, up->ev[i], 0));
+        Gemm g;
+        g.ta = 'N'; g.tb = 'N'; g.m = m; g.n = l; g.k = w; g.A = A + c0 * lda; g.lda = lda; g.C = Y; g.ldc = ldy;
+        g.beta = (i == 0) ? 0.0 : 1.0;
+        g.philox = true; g.seed = seed; g.ph_sk = 1; g.ph_sc = n; g.ph_off = off + c0;
+        gemm(g);
+    }
+}
+
+// `Y0` (optional): an already computed sketch A*Omega (m x l, ld m).  `up` (optional): A is still being uploaded in column chunks.
+int svd_rand_impl(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int vnum, int q, int s, uint64_t seed,
+                  const double *omega, DBuf *Y0, const Upload *up, double *U, i64 ldu, double *S, double *V, i64 ldv) {
     ensure_init();
     if (!ctx().inited) return 1;
     const i64 l = k + p;
@@ -165,7 +204,7 @@ static int svd_rand_impl(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, i
     else {
         Y.alloc((size_t)m * l);
         if (omega) mm('N', 'N', m, l, n, 1.0, A, lda, omega, n, 0.0, Y.p, m);       // Y = M RN (RRA:95)
-        else sketch('N', m, l, n, A, lda, seed, 1, n, 0, Y.p, m);                   // RN generated in the B-operand producer
+        else sketch_chunked(A, m, n, lda, l, seed, 0, Y.p, m, up);                  // RN generated in the B-operand producer
     }
     ph.lap("Y = A Omega (sketch)");
     for (int j = 1; j < q; ++j) {                                                   // NOTE j < q (RRA:101)
@@ -187,42 +226,20 @@ static int svd_rand_impl(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, i
 
 int svd_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int vnum, int q, int s, uint64_t seed,
              const double *omega, double *U, i64 ldu, double *S, double *V, i64 ldv) {
-    return svd_rand_impl(A, m, n, lda, k, p, vnum, q, s, seed, omega, nullptr, U, ldu, S, V, ldv);
+    return svd_rand_impl(A, m, n, lda, k, p, vnum, q, s, seed, omega, nullptr, nullptr, U, ldu, S, V, ldv);
 }
 
-// Same algorithm from a HOST matrix (pinned memory): A is uploaded in column blocks on the copy stream while the sketch
-// pass consumes the blocks that have landed (Y += A(:,blk) * Omega(blk,:), Omega generated in the kernel), so the first of
-// the 2q passes hides behind the PCIe transfer.  dA (m x n, ld m) receives the uploaded matrix.
+// Same algorithm from a HOST matrix: the upload (hostapi.cu: upload_begin) runs in column chunks on the copy stream while
+// the sketch pass consumes the chunks that have landed.  dA (m x n, ld m) receives the uploaded matrix.
 int svd_rand_host(const double *hA, double *dA, i64 m, i64 n, i64 k, i64 p, int vnum, int q, int s, uint64_t seed,
                   double *U, i64 ldu, double *S, double *V, i64 ldv) {
     ensure_init();
-    Ctx &c = ctx();
-    if (!c.inited) return 1;
-    const i64 l = k + p;
-    if (k <= 0 || p < 0 || l > n || s <= 0) { set_error("rsvd_b200: invalid parameters k=%lld p=%lld s=%d (need 0 < k+p <= n, s > 0)", (long long)k, (long long)p, s); return 1; }
-    DBuf Y((size_t)m * l);
-    i64 cw = ((i64)(384ll << 20) / (8 * m)) / 16 * 16;     // ~384 MB column blocks, multiples of the GEMM's k-tile
-    if (cw < 256) cw = 256;
-    const int nchunks = (int)((n + cw - 1) / cw);
-    std::vector<cudaEvent_t> ev((size_t)nchunks);
-    for (int i = 0; i < nchunks; ++i) {
-        const i64 c0 = (i64)i * cw, w = std::min(cw, n - c0);
-        RSVD_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-        RSVD_CUDA(cudaMemcpyAsync(dA + c0 * m, hA + c0 * m, (size_t)w * m * 8, cudaMemcpyHostToDevice, c.copy_stream));
-        RSVD_CUDA(cudaEventRecord(ev[i], c.copy_stream));
-    }
-    for (int i = 0; i < nchunks; ++i) {
-        const i64 c0 = (i64)i * cw, w = std::min(cw, n - c0);
-        RSVD_CUDA(cudaStreamWaitEvent(c.stream, ev[i], 0));
-        Gemm g;
-        g.ta = 'N'; g.tb = 'N'; g.m = m; g.n = l; g.k = w; g.A = dA + c0 * m; g.lda = m; g.C = Y.p; g.ldc = m;
-        g.beta = (i == 0) ? 0.0 : 1.0;
-        g.philox = true; g.seed = seed; g.ph_sk = 1; g.ph_sc = n; g.ph_off = c0;     // Omega(c0 + kk, j) = normal(seed, c0 + kk + j*n)
-        gemm(g);
-    }
-    RSVD_CUDA(cudaStreamSynchronize(c.stream));
-    for (auto &e : ev) cudaEventDestroy(e);
-    return svd_rand_impl(dA, m, n, m, k, p, vnum, q, s, seed, nullptr, &Y, U, ldu, S, V, ldv);
+    if (!ctx().inited) return 1;
+    Upload up;
+    upload_begin(hA, m, dA, m, n, up);
+    int rc = svd_rand_impl(dA, m, n, m, k, p, vnum, q, s, seed, nullptr, nullptr, &up, U, ldu, S, V, ldv);
+    upload_end(up);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -231,7 +248,7 @@ int svd_rand_host(const double *hA, double *dA, i64 m, i64 n, i64 k, i64 p, int 
 // legacy_reorth: re-orthogonalise Qp against Q(:, 0:c0) on EVERY step > 0 as randQB_pb does (RRA:1503-1528) instead of on
 // even steps only (randQB_pb_new, RRA:1703).
 int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, int q, int s, uint64_t seed,
-           double *Q, i64 ldq, double *B, i64 ldb, i64 max_rank, i64 *frank_out, int legacy_reorth) {
+           double *Q, i64 ldq, double *B, i64 ldb, i64 max_rank, i64 *frank_out, int legacy_reorth, const Upload *up) {
     ensure_init();
     Ctx &c = ctx();
     if (!c.inited) return 1;
@@ -244,7 +261,7 @@ int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, i
     i64 frank = 0;
     for (i64 step = 0; step < nstep; ++step) {                                      // RRA:1635
         const i64 c0 = kstep * step;
-        sketch('N', m, kstep, n, A, lda, seed, 1, n, c0 * n, Yp.p, m);              // Yp = A RN(:,block) (RRA:1643-1644)
+        sketch_chunked(A, m, n, lda, kstep, seed, c0 * n, Yp.p, m, step == 0 ? up : nullptr);   // Yp = A RN(:,block) (RRA:1643-1644)
         for (int j = 1; j <= q; ++j) {                                              // NOTE j <= q (RRA:1652)
             if ((2 * j - 2) % s == 0) orthonormalize(Yp.p, m, m, kstep, nullptr, 0, true, true);   // RRA:1655
             mm('T', 'N', n, kstep, m, 1.0, A, lda, Yp.p, m, 0.0, W.p, n);           // AtQp (RRA:1657-1658 / 1665)
@@ -268,14 +285,20 @@ int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, i
             allreduce_sum(t.p, (size_t)kstep * n);
             copy_matrix(t.p, kstep, Bp, ldb, kstep, n);
         }
-        mm('N', 'N', m, n, kstep, -1.0, Yp.p, m, Bp, ldb, 1.0, A, lda);             // A = A - Qp Bp (RRA:1750-1751)
+        {   // A = A - Qp Bp (RRA:1750-1751); in tolerance mode the epilogue also accumulates ||A - Qp Bp||_F^2 (RRA:1771),
+            // so the residual norm costs no extra 8mn-byte pass
+            Gemm g;
+            g.ta = 'N'; g.tb = 'N'; g.m = m; g.n = n; g.k = kstep; g.alpha = -1.0; g.beta = 1.0;
+            g.A = Yp.p; g.lda = m; g.B = Bp; g.ldb = ldb; g.C = A; g.ldc = lda;
+            if (tolMode) g.sumsq_out = sums.p;
+            gemm(g);
+        }
         copy_matrix(Yp.p, m, Q + c0 * ldq, ldq, m, kstep);                          // Q(:,block) (RRA:1760)
         frank = (step + 1) * kstep;                                                 // RRA:1770
         if (tolMode) {                                                              // RRA:1771-1777 (absolute Frobenius norm)
-            sumsq_async(A, lda, m, n, sums.p);
             allreduce_sum(sums.p, 1);
-            tol_check_kernel<<<1, 1, 0, c.stream>>>(sums.p, tol, done, sums.p + 1);
-            count_launch();
+            tol_check_kernel<<<1, 1, 0, c.stream>>>(sums.p, tol, done, sums.p + 1); // the test itself is evaluated on the device;
+            count_launch();                                                         // the host reads back 4 bytes to end the loop
             RSVD_CUDA(cudaMemcpyAsync(c.h_flag + 24, done, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
             RSVD_CUDA(cudaStreamSynchronize(c.stream));
             if (c.verbose) {
@@ -304,7 +327,7 @@ static void id_tail(double *Y, i64 ldy, i64 r, i64 n, i64 k, double *I, double *
 }
 
 int id_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, const double *omega,
-            double *I, double *T, i64 ldt) {
+            double *I, double *T, i64 ldt, const Upload *up) {
     ensure_init();
     Ctx &c = ctx();
     if (!c.inited) return 1;
@@ -315,6 +338,13 @@ int id_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, 
     DBuf Yt((size_t)n * l), Wt((size_t)m * l);
     if (omega) {   // omega is the reference's RN, l x m column-major (global rows; this rank uses columns row0..row0+m)
         mm('T', 'T', n, l, m, 1.0, A, lda, omega + c.row0 * l, l, 0.0, Yt.p, n);
+    } else if (up && !up->ev.empty()) {
+        // A is still arriving in column chunks: rows [c0, c0+w) of Yt = A(:, chunk)^T RN^T need only that chunk
+        for (size_t i = 0; i < up->ev.size(); ++i) {
+            const i64 c0 = (i64)i * up->cw, w = std::min(up->cw, n - c0);
+            RSVD_CUDA(cudaStreamWaitEvent(c.stream, up->ev[i], 0));
+            sketch('T', w, l, m, A + c0 * lda, lda, seed, l, 1, c.row0 * l, Yt.p + c0, n);
+        }
     } else {
         sketch('T', n, l, m, A, lda, seed, l, 1, c.row0 * l, Yt.p, n);              // Y = RN M (RRA:1877), RN(c,i) at i*l + c
     }
@@ -381,8 +411,8 @@ int id_rows(const double *A, i64 m, i64 n, i64 lda, const double *Icol, i64 k, d
 }
 
 int id_two_sided_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed,
-                      double *Icol, double *Irow, double *T, i64 ldt, double *S, i64 lds, i64 m_global) {
-    if (id_rand(A, m, n, lda, k, p, q, s, seed, nullptr, Icol, T, ldt)) return 1;  // RRA:2068
+                      double *Icol, double *Irow, double *T, i64 ldt, double *S, i64 lds, i64 m_global, const Upload *up) {
+    if (id_rand(A, m, n, lda, k, p, q, s, seed, nullptr, Icol, T, ldt, up)) return 1;  // RRA:2068
     return id_rows(A, m, n, lda, Icol, k, Irow, S, lds, m_global);
 }
 
@@ -423,11 +453,11 @@ int cur_from_id(const double *A, i64 m, i64 n, i64 lda, const double *Icol, cons
 }
 
 int cur_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed,
-             double *Cm, i64 ldc, double *U, i64 ldu, double *R, i64 ldr, i64 m_global) {
+             double *Cm, i64 ldc, double *U, i64 ldu, double *R, i64 ldr, i64 m_global, const Upload *up) {
     ensure_init();
     if (!ctx().inited) return 1;
     DBuf Icol((size_t)n), Irow((size_t)m_global), T((size_t)k * max((i64)1, n - k)), S((size_t)k * max((i64)1, m_global - k));
-    if (id_two_sided_rand(A, m, n, lda, k, p, q, s, seed, Icol.p, Irow.p, T.p, k, S.p, k, m_global)) return 1;   // RRA:2198
+    if (id_two_sided_rand(A, m, n, lda, k, p, q, s, seed, Icol.p, Irow.p, T.p, k, S.p, k, m_global, up)) return 1;   // RRA:2198
     S.release();
     return cur_from_id(A, m, n, lda, Icol.p, Irow.p, T.p, k, k, Cm, ldc, U, ldu, R, ldr);
 }
@@ -573,7 +603,7 @@ int svd_rand_from_sketch(const double *A, i64 m, i64 n, i64 lda, double *Y, i64 
                          double *S, double *V, i64 ldv) {
     DBuf Y0((size_t)m * l);
     copy_matrix(Y, ldy, Y0.p, m, m, l);
-    return svd_rand_impl(A, m, n, lda, l, 0, 1, q, s, 0, nullptr, &Y0, U, ldu, S, V, ldv);
+    return svd_rand_impl(A, m, n, lda, l, 0, 1, q, s, 0, nullptr, &Y0, nullptr, U, ldu, S, V, ldv);
 }
 
 // streamed 100*||A - U diag(S) V^T||_F / ||A||_F

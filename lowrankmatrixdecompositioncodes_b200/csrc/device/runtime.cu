@@ -10,6 +10,8 @@
 namespace rsvd {
 
 int g_status = 0;
+unsigned long long g_launches = 0;
+int g_single_device = 0;
 static char g_errbuf[1024] = "";
 static std::mutex g_err_mu;
 
@@ -25,13 +27,18 @@ void set_error(const char *fmt, ...) {
     }
 }
 
-Ctx &ctx() {
-    static Ctx c;
-    return c;
+// One context per (thread, device).  The calling thread of a C driver uses the primary context; in single-process
+// multi-GPU mode (multi.cu) every worker thread binds its own context, so all of the device layer below ctx() is
+// device-agnostic and re-entrant across workers.
+static Ctx g_ctx0;
+static thread_local Ctx *t_ctx = nullptr;
+Ctx &ctx() { return t_ctx ? *t_ctx : g_ctx0; }
+void bind_ctx(Ctx *c) {
+    t_ctx = c;
+    if (c && c->device >= 0) cudaSetDevice(c->device);
 }
 
-static int init_device(int device) {
-    Ctx &c = ctx();
+int init_ctx(Ctx &c, int device) {
     if (c.inited) return 0;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -43,7 +50,8 @@ static int init_device(int device) {
     if (device < 0) {
         const char *s = getenv("RSVD_B200_DEVICE");
         if (!s) s = getenv("LOCAL_RANK");
-        device = s ? atoi(s) : 0;
+        if (!s) s = getenv("RSVD_B200_DEVICES");            // "0-7" / "2,3": the primary context sits on the first listed device
+        device = (s && *s >= '0' && *s <= '9') ? atoi(s) : 0;
         if (device >= ndev) device = device % ndev;
     }
     RSVD_CUDA(cudaSetDevice(device));
@@ -72,6 +80,7 @@ static int init_device(int device) {
     c.inited = (g_status == 0);
     return g_status;
 }
+static int init_device(int device) { return init_ctx(ctx(), device); }
 
 void ensure_init() {
     if (!ctx().inited) init_device(-1);
@@ -118,7 +127,12 @@ struct Staging {
         ok = true;
     }
 };
-static Staging g_staging;
+static Staging &staging() {
+    Ctx &c = ctx();
+    if (!c.staging) c.staging = new Staging();
+    return *(Staging *)c.staging;
+}
+#define g_staging (staging())
 
 static int copy_h2d(double *d, const double *h, size_t n) {
     ensure_init();
@@ -198,7 +212,7 @@ const char *rsvd_b200_last_error(void) { return g_errbuf; }
 void rsvd_b200_clear_error(void) { g_status = 0; g_errbuf[0] = 0; }
 void *rsvd_b200_stream(void) { ensure_init(); return (void *)ctx().stream; }
 void rsvd_b200_sync(void) { if (ctx().inited) RSVD_CUDA(cudaStreamSynchronize(ctx().stream)); }
-unsigned long long rsvd_b200_launch_count(void) { return ctx().launches; }
+unsigned long long rsvd_b200_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 static unsigned long long g_seed_opt = 777ull;
 void rsvd_b200_set_option(const char *name, rsvd_i64 value) {
@@ -209,6 +223,7 @@ void rsvd_b200_set_option(const char *name, rsvd_i64 value) {
     else if (!strcmp(name, "row0")) ctx().row0 = value;
     else if (!strcmp(name, "jacobi_transpose")) ctx().jacobi_transpose = (int)value;
     else if (!strcmp(name, "m_global")) ctx().m_global = value;
+    else if (!strcmp(name, "single_device")) g_single_device = (int)value;
     else set_error("rsvd_b200_set_option: unknown option '%s'", name);
 }
 rsvd_i64 rsvd_b200_get_option(const char *name) {
@@ -224,6 +239,8 @@ rsvd_i64 rsvd_b200_get_option(const char *name) {
     if (!strcmp(name, "row0")) return ctx().row0;
     if (!strcmp(name, "m_global")) return ctx().m_global;
     if (!strcmp(name, "world")) return ctx().world;
+    if (!strcmp(name, "single_device")) return g_single_device;
+    if (!strcmp(name, "devices")) return pool_size();
     return -1;
 }
 
@@ -322,7 +339,7 @@ void *rsvd_b200_host_alloc(size_t bytes) {
     ensure_init();
     if (!ctx().inited) return nullptr;
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 8, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 8, cudaHostAllocPortable) != cudaSuccess) {   // pinned for every device (multi-GPU uploads)
         (void)cudaGetLastError();
         return nullptr;
     }

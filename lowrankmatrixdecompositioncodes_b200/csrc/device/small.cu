@@ -156,10 +156,10 @@ __global__ void sumsq_partial_kernel(const double *__restrict__ A, i64 lda, i64 
         if (threadIdx.x == 0) part[blockIdx.x] = s;
     }
 }
-__global__ void sum_final_kernel(const double *__restrict__ part, int n, double *out) {
+__global__ void sum_final_kernel(const double *__restrict__ part, i64 n, double *out) {
     __shared__ double sh[32];
     double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+    for (i64 i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
@@ -178,6 +178,11 @@ void sumsq_async(const double *A, i64 lda, i64 m, i64 n, double *d_out) {
     sumsq_partial_kernel<<<blocks, 512, 0, ctx().stream>>>(A, lda, m, n, part.p);
     sum_final_kernel<<<1, 256, 0, ctx().stream>>>(part.p, blocks, d_out);
     count_launch(2);
+}
+void sum_array_async(const double *part, i64 n, double *d_out) {
+    if (g_status) return;
+    sum_final_kernel<<<1, 1024, 0, ctx().stream>>>(part, n, d_out);
+    count_launch();
 }
 double frob_norm(const double *A, i64 lda, i64 m, i64 n) {
     ensure_init();

@@ -14,6 +14,9 @@ typedef RSVD_INT idx_t;
 /* ---- allocation: large matrices live in pinned memory so uploads/downloads run at PCIe speed.  Pinning costs
  * ~0.5 ms/MB, so released pinned blocks are kept in a small cache (<= 1 GiB) and reused by later matrix_new calls
  * (repeated API calls then allocate their U/V outputs for free). ---------------------------------------------------- */
+#include <pthread.h>
+/* reference drivers call vector_new / vector_delete inside omp parallel loops: the tables below are shared state */
+static pthread_mutex_t g_tab_mu = PTHREAD_MUTEX_INITIALIZER;
 #define PINNED_MAX 256
 static void *g_pinned[PINNED_MAX];
 static size_t g_pinned_bytes[PINNED_MAX];
@@ -35,37 +38,53 @@ static size_t pinned_threshold(void) {
  * clearing 280 MB of outputs cost 19 of the 24 ms "download" phase of an end-to-end call at BASELINE configs[1]. */
 static double *host_alloc_impl(size_t n, int zero) {
     size_t bytes = n * sizeof(double);
-    if (bytes >= pinned_threshold() && g_npinned < PINNED_MAX && rsvd_b200_device_count() > 0) {
+    if (bytes >= pinned_threshold() && rsvd_b200_device_count() > 0) {   /* small allocations never touch the tables */
         void *p = NULL;
+        pthread_mutex_lock(&g_tab_mu);
+        if (g_npinned >= PINNED_MAX) { pthread_mutex_unlock(&g_tab_mu); return (double *)calloc(n ? n : 1, sizeof(double)); }
         for (int i = 0; i < g_ncache; ++i)
             if (g_cache_bytes[i] >= bytes && g_cache_bytes[i] <= bytes + (bytes >> 3)) {   /* reuse a cached block of ~the same size */
                 p = g_cache[i];
                 size_t cb = g_cache_bytes[i];
                 g_cache_total -= cb;
                 g_cache[i] = g_cache[g_ncache - 1]; g_cache_bytes[i] = g_cache_bytes[g_ncache - 1]; --g_ncache;
-                if (zero) memset(p, 0, bytes);
                 g_pinned[g_npinned] = p; g_pinned_bytes[g_npinned++] = cb;
+                pthread_mutex_unlock(&g_tab_mu);
+                if (zero) memset(p, 0, bytes);
                 return (double *)p;
             }
+        pthread_mutex_unlock(&g_tab_mu);
         p = rsvd_b200_host_alloc(bytes);
-        if (p) { g_pinned[g_npinned] = p; g_pinned_bytes[g_npinned++] = bytes; return (double *)p; }
+        if (p) {
+            pthread_mutex_lock(&g_tab_mu);
+            if (g_npinned < PINNED_MAX) { g_pinned[g_npinned] = p; g_pinned_bytes[g_npinned++] = bytes; pthread_mutex_unlock(&g_tab_mu); return (double *)p; }
+            pthread_mutex_unlock(&g_tab_mu);
+            rsvd_b200_host_free(p);
+        }
     }
     return (double *)calloc(n ? n : 1, sizeof(double));
 }
 double *rsvd_host_calloc(size_t n) { return host_alloc_impl(n, 1); }
 double *rsvd_host_alloc_uninit(size_t n) { return host_alloc_impl(n, 0); }
 void rsvd_host_free(double *p) {
-    for (int i = 0; i < g_npinned; ++i)
-        if (g_pinned[i] == (void *)p) {
-            size_t bytes = g_pinned_bytes[i];
-            g_pinned[i] = g_pinned[g_npinned - 1]; g_pinned_bytes[i] = g_pinned_bytes[g_npinned - 1]; --g_npinned;
-            if (g_ncache < CACHE_MAX && g_cache_total + bytes <= ((size_t)1 << 30)) {
-                g_cache[g_ncache] = p; g_cache_bytes[g_ncache++] = bytes; g_cache_total += bytes;
-            } else {
-                rsvd_b200_host_free(p);
+    if (!p) return;
+    if (__atomic_load_n(&g_npinned, __ATOMIC_RELAXED) > 0) {     /* a pinned block is only ever freed by the thread that holds it */
+        pthread_mutex_lock(&g_tab_mu);
+        for (int i = 0; i < g_npinned; ++i)
+            if (g_pinned[i] == (void *)p) {
+                size_t bytes = g_pinned_bytes[i];
+                int keep = 0;
+                g_pinned[i] = g_pinned[g_npinned - 1]; g_pinned_bytes[i] = g_pinned_bytes[g_npinned - 1]; --g_npinned;
+                if (g_ncache < CACHE_MAX && g_cache_total + bytes <= ((size_t)1 << 30)) {
+                    g_cache[g_ncache] = p; g_cache_bytes[g_ncache++] = bytes; g_cache_total += bytes;
+                    keep = 1;
+                }
+                pthread_mutex_unlock(&g_tab_mu);
+                if (!keep) rsvd_b200_host_free(p);
+                return;
             }
-            return;
-        }
+        pthread_mutex_unlock(&g_tab_mu);
+    }
     free(p);
 }
 
@@ -297,6 +316,7 @@ void rsvd_download(double *h, const double *d, size_t n) {
 }
 
 void initialize_random_matrix(mat *M) {
+    rsvd_api_begin();   /* a failure of an EARLIER top-level call must not turn this one into a silent no-op */
     size_t N = (size_t)M->nrows * (size_t)M->ncols;
     double *d = rsvd_b200_dev_alloc((rsvd_i64)(N ? N : 1));
     if (!d) { rsvd_api_sync_error(); return; }
@@ -307,6 +327,7 @@ void initialize_random_matrix(mat *M) {
 }
 
 static void host_gemm(char ta, char tb, mat *A, mat *B, mat *C) {
+    rsvd_api_begin();   /* a failure of an EARLIER top-level call must not turn this one into a silent no-op */
     idx_t m = C->nrows, n = C->ncols, k = (ta == 'N') ? A->ncols : A->nrows;
     double *dA = rsvd_upload(A->d, (size_t)A->nrows * (size_t)A->ncols);
     double *dB = rsvd_upload(B->d, (size_t)B->nrows * (size_t)B->ncols);
@@ -434,6 +455,7 @@ void vector_build_rewrapped(vec *Iinv, vec *I) {
 
 /* ---- factorizations on the device -------------------------------------------------------------------------------- */
 void compute_evals_and_evecs_of_symm_matrix(mat *S, vec *evals) {
+    rsvd_api_begin();   /* a failure of an EARLIER top-level call must not turn this one into a silent no-op */
     idx_t n = S->nrows;
     /* dsyev 'U' reads only the upper triangle (callers fill it with matrix_copy_symmetric): mirror it first */
     for (idx_t j = 0; j < n; ++j)
@@ -450,6 +472,7 @@ void compute_evals_and_evecs_of_symm_matrix(mat *S, vec *evals) {
 }
 
 static void host_qr(mat *M, mat *Q, mat *R) {
+    rsvd_api_begin();   /* a failure of an EARLIER top-level call must not turn this one into a silent no-op */
     idx_t m = M->nrows, n = M->ncols;
     if (m < n) { rsvd_api_error("QR of a %lld x %lld matrix: only tall panels (m >= n) are supported", (long long)m, (long long)n); return; }
     double *dY = rsvd_upload(M->d, (size_t)m * (size_t)n);
@@ -468,6 +491,7 @@ void QR_factorization_getQ(mat *M, mat *Q) { host_qr(M, Q, NULL); }
 /* MVF:1270-1284 (dgesvd 'S','S'): U m x r, S r x r diagonal, Vt r x n, r = min(m,n).  Square inputs (the hot path's l x l
  * Rhat) go straight to the Jacobi kernel; other shapes through the QR-preconditioned full SVD. */
 void singular_value_decomposition(mat *M, mat *U, mat *S, mat *Vt) {
+    rsvd_api_begin();   /* a failure of an EARLIER top-level call must not turn this one into a silent no-op */
     idx_t m = M->nrows, n = M->ncols, r = min(m, n);
     double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
     double *dU = rsvd_b200_dev_alloc((rsvd_i64)m * r + 1), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * r + 1), *ds = rsvd_b200_dev_alloc(r + 1);
@@ -492,19 +516,24 @@ void singular_value_decomposition(mat *M, mat *U, mat *S, mat *Vt) {
 }
 
 void form_svd_product_matrix(mat *U, mat *S, mat *V, mat *P) {
+    rsvd_api_enter();
     mat *SVt = matrix_new(S->nrows, P->ncols);
     matrix_matrix_transpose_mult(S, V, SVt);
     matrix_matrix_mult(U, SVt, P);
     matrix_delete(SVt);
+    rsvd_api_leave();
 }
 void form_cur_product_matrix(mat *C, mat *U, mat *R, mat *P) {
+    rsvd_api_enter();
     mat *CU = matrix_new(P->nrows, U->nrows);
     matrix_matrix_mult(C, U, CU);
     matrix_matrix_mult(CU, R, P);
     matrix_delete(CU);
+    rsvd_api_leave();
 }
 
 void upper_triangular_system_solve(mat *A, mat *B, mat *X, int solve_type) {
+    rsvd_api_begin();   /* a failure of an EARLIER top-level call must not turn this one into a silent no-op */
     (void)solve_type;   /* the reference's variants 1-4 all compute A^{-1} B; one device solver serves them */
     idx_t k = A->nrows, nc = B->ncols;
     double *dA = rsvd_upload(A->d, (size_t)k * (size_t)k);
@@ -518,6 +547,7 @@ void upper_triangular_system_solve(mat *A, mat *B, mat *X, int solve_type) {
 }
 
 void square_matrix_system_solve(mat *A, mat *X, mat *B) {
+    rsvd_api_begin();   /* a failure of an EARLIER top-level call must not turn this one into a silent no-op */
     idx_t n = A->nrows, nc = B->ncols;
     double *dA = rsvd_upload(A->d, (size_t)n * (size_t)n);
     double *dB = rsvd_upload(B->d, (size_t)n * (size_t)nc);
@@ -545,6 +575,7 @@ void build_orthonormal_basis_from_mat(mat *A, mat *Q) { host_qr(A, Q, NULL); }
 
 /* MVF:1339-1400 */
 void estimate_rank_and_buildQ(mat *M, double frac_of_max_rank, double TOL, mat **Q, idx_t *good_rank) {
+    rsvd_api_begin();   /* a failure of an EARLIER top-level call must not turn this one into a silent no-op */
     idx_t m = M->nrows, n = M->ncols;
     idx_t maxdim = (idx_t)llround((double)min(m, n) * frac_of_max_rank);
     *Q = NULL; *good_rank = 0;
@@ -563,6 +594,7 @@ void estimate_rank_and_buildQ(mat *M, double frac_of_max_rank, double TOL, mat *
 
 /* MVF:1404-1467 */
 void estimate_rank_and_buildQ2(mat *M, idx_t kblock, double TOL, mat **Y, mat **Q, idx_t *good_rank) {
+    rsvd_api_begin();   /* a failure of an EARLIER top-level call must not turn this one into a silent no-op */
     idx_t m = M->nrows, n = M->ncols, r = min(m, n);
     *Y = NULL; *Q = NULL; *good_rank = 0;
     if (kblock <= 0 || kblock > r) { rsvd_api_error("estimate_rank_and_buildQ2: need 0 < kblock <= min(m,n)"); *Y = matrix_new(m, 0); *Q = matrix_new(m, 0); return; }

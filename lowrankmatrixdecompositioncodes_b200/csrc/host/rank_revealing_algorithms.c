@@ -14,6 +14,7 @@ typedef RSVD_INT idx_t;
 static int g_api_status = 0;
 static char g_api_err[1024] = "";
 static double g_last_percent_error = -1.0;
+static char g_api_warn[512];
 
 void rsvd_api_error(const char *fmt, ...) {
     if (g_api_status) return;
@@ -27,13 +28,26 @@ void rsvd_api_error(const char *fmt, ...) {
 void rsvd_api_sync_error(void) {
     if (rsvd_b200_status()) rsvd_api_error("%s", rsvd_b200_last_error());
 }
+static int g_api_depth = 0;                   /* > 0: inside a composite call (one exported function calling others) */
 void rsvd_api_begin(void) {
-    g_api_status = 0; g_api_err[0] = 0;
+    if (g_api_depth > 0) return;
+    g_api_status = 0; g_api_err[0] = 0; g_api_warn[0] = 0;
     rsvd_b200_clear_error();
 }
+void rsvd_api_enter(void) { rsvd_api_begin(); ++g_api_depth; }
+void rsvd_api_leave(void) { if (g_api_depth > 0) --g_api_depth; }
 int rsvd_b200_api_status(void) { rsvd_api_sync_error(); return g_api_status; }
-void rsvd_b200_api_clear_error(void) { rsvd_api_begin(); }   /* the helpers of matrix_vector_functions do not reset the status themselves */
+void rsvd_b200_api_clear_error(void) { g_api_depth = 0; rsvd_api_begin(); }   /* the helpers of matrix_vector_functions do not reset the status themselves */
 const char *rsvd_b200_api_last_error(void) { return g_api_err; }
+/* warnings (an argument was adjusted, the call went ahead): recorded, never turned into an error status */
+static void rsvd_api_warning(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_api_warn, sizeof(g_api_warn), fmt, ap);
+    va_end(ap);
+    if (getenv("RSVD_B200_VERBOSE")) fprintf(stderr, "[rsvd_b200 api] warning: %s\n", g_api_warn);
+}
+const char *rsvd_b200_api_last_warning(void) { return g_api_warn; }
 double rsvd_b200_api_last_percent_error(void) { return g_last_percent_error; }
 
 static int verbose(void) {
@@ -64,8 +78,18 @@ static mat *diag_from_device(const double *ds, idx_t k) {
     return S;
 }
 
+/* sets S (k x k, zeroed) to diag(s) */
+static void fill_diag(mat *S, const double *s, idx_t k) {
+    for (idx_t i = 0; i < k; ++i) S->d[(size_t)i * (size_t)k + (size_t)i] = s[i];
+}
+/* a failed call returns zeros, as documented */
+static void zero_mat(mat *M) { if (M && M->d) memset(M->d, 0, (size_t)M->nrows * (size_t)M->ncols * sizeof(double)); }
+static void zero_vec(vec *v) { if (v && v->d) memset(v->d, 0, (size_t)v->nrows * sizeof(double)); }
+
 /* ---- low_rank_svd_rand_decomp_fixed_rank (RRA:73-234) -------------------------------------------------------------
- * *frank is never written by the reference; neither here. */
+ * *frank is never written by the reference; neither here.  One host-level call: the upload of M is
+ * pipelined with the sketch pass, all 2q passes run on the resident copy (row-partitioned over the active devices when
+ * RSVD_B200_DEVICES lists several), the factors are downloaded straight into the callee-allocated outputs. */
 void low_rank_svd_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t vnum, idx_t q, idx_t s, idx_t *frank,
                                          mat **U, mat **S, mat **V) {
     (void)frank;
@@ -78,31 +102,26 @@ void low_rank_svd_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t vnum, i
         *U = matrix_new(m, max(k, 0)); *S = matrix_new(max(k, 0), max(k, 0)); *V = matrix_new(n, max(k, 0));
         return;
     }
-    struct timeval t0, t1, t2, t3;
+    struct timeval t0, t1, t2;
     gettimeofday(&t0, NULL);
-    double *dA = rsvd_b200_dev_alloc((rsvd_i64)m * n);
-    double *dU = rsvd_b200_dev_alloc((rsvd_i64)m * k), *dS = rsvd_b200_dev_alloc(k), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * k);
+    *U = rsvd_matrix_new_uninit(m, k); *S = matrix_new(k, k); *V = rsvd_matrix_new_uninit(n, k);   /* U, V are fully overwritten */
+    double *sv = (double *)calloc((size_t)k, sizeof(double));
     gettimeofday(&t1, NULL);
-    if (dA && dU && dS && dV)   /* upload of M overlapped with the sketch pass */
-        rsvd_b200_svd_rand_host(M->d, dA, m, n, k, p, (int)vnum, (int)q, (int)s, omega_seed(), dU, m, dS, dV, n);
-    rsvd_b200_sync();
+    rsvd_b200_svd_rand_h(M->d, m, n, m, k, p, (int)vnum, (int)q, (int)s, omega_seed(), (*U)->d, m, sv, (*V)->d, n);
     gettimeofday(&t2, NULL);
-    rsvd_b200_dev_free(dA);
-    *U = download_mat(dU, m, k);
-    *S = diag_from_device(dS, k);
-    *V = download_mat(dV, n, k);
-    gettimeofday(&t3, NULL);
-    if (verbose())
-        fprintf(stderr, "[rsvd_b200 api] alloc %.3f s, upload+device %.3f s, alloc+download %.3f s\n", get_seconds_frac(t0, t1),
-                get_seconds_frac(t1, t2), get_seconds_frac(t2, t3));
-    rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dS); rsvd_b200_dev_free(dV);
     rsvd_api_sync_error();
+    if (g_api_status) { zero_mat(*U); zero_mat(*V); }
+    else fill_diag(*S, sv, k);
+    free(sv);
+    if (verbose())
+        fprintf(stderr, "[rsvd_b200 api] output allocation %.3f s, upload + device + download %.3f s\n", get_seconds_frac(t0, t1), get_seconds_frac(t1, t2));
 }
 
 /* ---- randQB_pb_new (RRA:1576-1801) -------------------------------------------------------------------------------- */
-static int randqb_device(mat *M, idx_t kstep, idx_t nstep, double TOL, idx_t q, idx_t s, idx_t *frank,
-                         double **dA_out, double **dQ_out, double **dB_out, idx_t *cap_out) {
+/* Runs the blocked QB on the device(s); Q, B and the residual stay in HBM behind *qb_out. */
+static int randqb_device(mat *M, idx_t kstep, idx_t nstep, double TOL, idx_t q, idx_t s, idx_t *frank, void **qb_out, idx_t *cap_out) {
     idx_t m = M->nrows, n = M->ncols, r = min(m, n);
+    *qb_out = NULL; *cap_out = 0; *frank = 0;
     if (kstep > (idx_t)(r / 2)) {                       /* RRA:1589-1592 */
         kstep = (idx_t)r / 10;
         if (verbose()) printf("kstep resized to %lld\n", (long long)kstep);
@@ -112,13 +131,10 @@ static int randqb_device(mat *M, idx_t kstep, idx_t nstep, double TOL, idx_t q, 
     if (nstep <= 0) cap = (idx_t)(r / kstep) * kstep;   /* tolerance mode (RRA:1595-1602) */
     else cap = kstep * nstep;
     if (cap > r) cap = (r / kstep) * kstep;
-    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);   /* the private copy A = M (RRA:1630) lives only in HBM */
-    double *dQ = rsvd_b200_dev_alloc((rsvd_i64)m * cap + 1), *dB = rsvd_b200_dev_alloc((rsvd_i64)cap * n + 1);
     rsvd_i64 fr = 0;
-    if (dA && dQ && dB)
-        rsvd_b200_randqb_dev(dA, m, n, m, kstep, nstep <= 0 ? 0 : cap / kstep, TOL, (int)q, (int)s, omega_seed(), dQ, m, dB, cap, &fr);
+    void *qb = rsvd_b200_randqb_h(M->d, m, n, m, kstep, nstep <= 0 ? 0 : cap / kstep, cap, TOL, (int)q, (int)s, omega_seed(), &fr);
     *frank = (idx_t)fr;
-    *dA_out = dA; *dQ_out = dQ; *dB_out = dB; *cap_out = cap;
+    *qb_out = qb; *cap_out = cap;
     rsvd_api_sync_error();
     return g_api_status;
 }
@@ -126,66 +142,64 @@ static int randqb_device(mat *M, idx_t kstep, idx_t nstep, double TOL, idx_t q, 
 void randQB_pb_new(mat *M, idx_t kstep, idx_t nstep, double TOL, idx_t q, idx_t s, idx_t *frank, mat **Q, mat **B) {
     rsvd_api_begin();
     idx_t m = M->nrows, n = M->ncols, cap = 0;
-    double *dA = NULL, *dQ = NULL, *dB = NULL;
+    void *qb = NULL;
     *Q = NULL; *B = NULL;
-    randqb_device(M, kstep, nstep, TOL, q, s, frank, &dA, &dQ, &dB, &cap);
-    rsvd_b200_dev_free(dA);
+    if (randqb_device(M, kstep, nstep, TOL, q, s, frank, &qb, &cap)) {
+        rsvd_b200_qb_free(qb);
+        *Q = matrix_new(m, 0); *B = matrix_new(0, n);
+        return;
+    }
     /* rank mode returns all kstep*nstep columns; tolerance mode is cut to frank (RRA:1782-1789) */
     idx_t cols = (nstep <= 0) ? *frank : cap;
-    if (dQ && dB) {
-        *Q = download_mat(dQ, m, cols);
-        mat *Bfull = download_mat(dB, cap, n);
-        if (cols != cap) resize_matrix_by_rows(&Bfull, cols);
-        *B = Bfull;
-    } else {
-        *Q = matrix_new(m, 0); *B = matrix_new(0, n);
-    }
-    rsvd_b200_dev_free(dQ); rsvd_b200_dev_free(dB);
+    *Q = rsvd_matrix_new_uninit(m, cols); *B = rsvd_matrix_new_uninit(cols, n);
+    rsvd_b200_qb_download(qb, cols, (*Q)->d, m, (*B)->d, cols);
+    rsvd_b200_qb_free(qb);
     rsvd_api_sync_error();
+    if (g_api_status) { zero_mat(*Q); zero_mat(*B); }
 }
 
 /* ---- low_rank_svd_blockrand_decomp_fixed_rank_or_prec (RRA:239-381) -------------------------------------------------
- * Parameter handling follows the reference exactly, including quirk Q1: nstep = (k+p)/kstep by
- * INTEGER division is computed after the k<=0 branch, so tolerance mode is never reached through this entry point;
- * call randQB_pb_new(nstep <= 0) for a tolerance-driven QB. */
+ * Parameter handling follows the reference exactly, including quirk Q1: nstep = (k+p)/kstep by INTEGER
+ * division is computed after the k <= 0 branch and overwrites its nstep = 0, so for ordinary arguments the QB runs in rank
+ * mode; only when that division itself yields 0 (k = -1 with p <= kstep, or k = p = 0 with kstep >= min(m,n)/2, ...) does
+ * randQB_pb_new see nstep = 0 and run tolerance-driven, exactly as in the reference (RRA:251-266).
+ * The SVD tail (RRA:289-380: Bt = M^T Q, ...) works from the QB residual in HBM; M is not uploaded a second time. */
 void low_rank_svd_blockrand_decomp_fixed_rank_or_prec(mat *M, idx_t k, idx_t p, double TOL, idx_t vnum, idx_t kstep,
                                                       idx_t q, idx_t s, idx_t *frank, mat **U, mat **S, mat **V) {
     rsvd_api_begin();
     idx_t m = M->nrows, n = M->ncols;
     int rankMode = k > 0;
     if (p < kstep && (p + kstep) < min(m, n)) p = kstep;          /* RRA:260-262 */
-    idx_t nstep = (kstep > 0) ? (k + p) / kstep : 0;              /* RRA:263 */
+    idx_t nstep = (kstep > 0) ? (k + p) / kstep : 0;              /* RRA:263; <= 0: tolerance mode inside randQB_pb_new */
     *U = NULL; *S = NULL; *V = NULL;
-    if (nstep <= 0) { rsvd_api_error("low_rank_svd_blockrand: (k+p)/kstep = 0 blocks"); *U = matrix_new(m, 0); *S = matrix_new(0, 0); *V = matrix_new(n, 0); return; }
     idx_t cap = 0, fr = 0;
-    double *dA = NULL, *dQ = NULL, *dB = NULL;
-    if (randqb_device(M, kstep, nstep, TOL, q, s, &fr, &dA, &dQ, &dB, &cap)) {
-        rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dQ); rsvd_b200_dev_free(dB);
+    void *qb = NULL;
+    if (randqb_device(M, kstep, nstep, TOL, q, s, &fr, &qb, &cap) || fr <= 0) {
+        if (!g_api_status) rsvd_api_error("low_rank_svd_blockrand: the QB produced no columns");
+        rsvd_b200_qb_free(qb);
         *U = matrix_new(m, 0); *S = matrix_new(0, 0); *V = matrix_new(n, 0);
         return;
     }
-    rsvd_b200_dev_free(dB);                                        /* the SVD tail recomputes from M and Q (RRA:289-380) */
-    idx_t l = cap;                                                 /* l = B->nrows (RRA:271) */
+    idx_t l = (nstep <= 0) ? fr : cap;                             /* l = B->nrows (RRA:271): tolerance mode cuts B to frank rows */
     if (rankMode) *frank = k;                                      /* RRA:274-275 */
     else *frank = (idx_t)round(((double)fr / ((double)fr + (double)p + 1e-6)) * (double)fr);   /* RRA:278 */
     idx_t kk = *frank;
     if (kk > l) kk = l;
-    /* the residual in dA is replaced by the original M for the tail */
-    if (rsvd_b200_h2d(dA, M->d, (rsvd_i64)m * n)) rsvd_api_sync_error();
-    double *dU = rsvd_b200_dev_alloc((rsvd_i64)m * kk + 1), *dS = rsvd_b200_dev_alloc(kk + 1), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * kk + 1);
-    if (dU && dS && dV) rsvd_b200_svd_from_q_dev(dA, m, n, m, dQ, m, l, kk, (int)vnum, dU, m, dS, dV, n);
-    rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dQ);
-    *U = download_mat(dU, m, kk);
-    *S = diag_from_device(dS, kk);
-    *V = download_mat(dV, n, kk);
-    rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dS); rsvd_b200_dev_free(dV);
+    if (kk <= 0) { rsvd_api_error("low_rank_svd_blockrand: rank %lld", (long long)kk); rsvd_b200_qb_free(qb); *U = matrix_new(m, 0); *S = matrix_new(0, 0); *V = matrix_new(n, 0); return; }
+    *U = rsvd_matrix_new_uninit(m, kk); *S = matrix_new(kk, kk); *V = rsvd_matrix_new_uninit(n, kk);
+    double *sv = (double *)calloc((size_t)kk, sizeof(double));
+    rsvd_b200_qb_svd(qb, l, kk, (int)vnum, (*U)->d, m, sv, (*V)->d, n);
+    rsvd_b200_qb_free(qb);
     rsvd_api_sync_error();
+    if (g_api_status) { zero_mat(*U); zero_mat(*V); }
+    else fill_diag(*S, sv, kk);
+    free(sv);
 }
 
 /* ---- pivotedQR_mkl (RRA:924-976) ------------------------------------------------------------------------------------
  * R and I come from the dgeqp3-compatible device kernel.  The reference also returns the explicit Q (never read on the
  * hot path); it is rebuilt here as M(:,I(1:k)) * R11^{-1}, which equals the Householder Q when R11 is nonsingular. */
-void pivotedQR_mkl(mat *M, mat **Q, mat **R, vec **I) {
+static void pivotedQR_mkl_impl(mat *M, mat **Q, mat **R, vec **I) {
     rsvd_api_begin();
     idx_t m = M->nrows, n = M->ncols, k = min(m, n);
     idx_t Rcols = (m <= n) ? n : k;
@@ -212,6 +226,11 @@ void pivotedQR_mkl(mat *M, mat **Q, mat **R, vec **I) {
     matrix_delete(MI); matrix_delete(R11); matrix_delete(R11inv); matrix_delete(Ik);
     rsvd_api_sync_error();
 }
+void pivotedQR_mkl(mat *M, mat **Q, mat **R, vec **I) {   /* composite: nested calls keep one status */
+    rsvd_api_enter();
+    pivotedQR_mkl_impl(M, Q, R, I);
+    rsvd_api_leave();
+}
 
 /* ---- ID family ---------------------------------------------------------------------------------------------------- */
 void id_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t q, idx_t s, vec **I, mat **T) {
@@ -223,14 +242,10 @@ void id_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t q, idx_t s, vec *
         *I = vector_new(n); *T = matrix_new(max(k, 0), n - max(k, 0));
         return;
     }
-    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
-    double *dI = rsvd_b200_dev_alloc(n + 1), *dT = rsvd_b200_dev_alloc((rsvd_i64)k * (n - k) + 1);
-    if (dA && dI && dT) rsvd_b200_id_rand_dev(dA, m, n, m, k, p, (int)q, (int)s, omega_seed(), NULL, dI, dT, k);
-    rsvd_b200_dev_free(dA);
-    *I = download_vec(dI, n);
-    *T = download_mat(dT, k, n - k);
-    rsvd_b200_dev_free(dI); rsvd_b200_dev_free(dT);
+    *I = vector_new(n); *T = matrix_new(k, n - k);
+    rsvd_b200_id_rand_h(M->d, m, n, m, k, p, (int)q, (int)s, omega_seed(), (*I)->d, (*T)->d, k);
     rsvd_api_sync_error();
+    if (g_api_status) { zero_vec(*I); zero_mat(*T); }
 }
 
 /* Runs the reference's own partial pivoted QR on the device and leaves I, R (kmax x n, ld kmax) there.  Returns frank. */
@@ -253,7 +268,7 @@ static idx_t pqr_device(mat *M, idx_t k, double TOL, int zero_exact, double **dI
 static void pqr_host(mat *M, idx_t k, double TOL, int zero_exact, const char *who, idx_t *frank, mat **Qk, mat **Rk, vec **I) {
     rsvd_api_begin();
     idx_t m = M->nrows, n = M->ncols, kmax = 0;
-    if (k > min(m, n)) rsvd_api_error("%s: k = %lld exceeds min(m,n) = %lld; clamped", who, (long long)k, (long long)min(m, n));
+    if (k > min(m, n)) rsvd_api_warning("%s: k = %lld exceeds min(m,n) = %lld; clamped", who, (long long)k, (long long)min(m, n));
     double *dI = NULL, *dQ = NULL, *dR = NULL;
     *frank = pqr_device(M, k, TOL, zero_exact, &dI, &dQ, &dR, &kmax);
     *I = download_vec(dI, n);
@@ -318,7 +333,7 @@ void id_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, vec
 }
 
 /* RRA:2034-2056: column ID of M, then the (full) row ID of M(:, Icol(1:frank))^T */
-void id_two_sided_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, vec **Icol, vec **Irow, mat **T, mat **S) {
+static void id_two_sided_decomp_fixed_rank_or_prec_impl(mat *M, idx_t k, double TOL, idx_t *frank, vec **Icol, vec **Irow, mat **T, mat **S) {
     idx_t m = M->nrows;
     id_decomp_fixed_rank_or_prec(M, k, TOL, frank, Icol, T);
     if (g_api_status) { *Irow = vector_new(m); *S = matrix_new(*frank, m - *frank); return; }
@@ -328,9 +343,14 @@ void id_two_sided_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *
     id_decomp_fixed_rank_or_prec(MIt, *frank, 0, frank, Irow, S);
     matrix_delete(MI); matrix_delete(MIt);
 }
+void id_two_sided_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, vec **Icol, vec **Irow, mat **T, mat **S) {   /* composite: nested calls keep one status */
+    rsvd_api_enter();
+    id_two_sided_decomp_fixed_rank_or_prec_impl(M, k, TOL, frank, Icol, Irow, T, S);
+    rsvd_api_leave();
+}
 
 /* RRA:2115-2187: two-sided ID, then the same CUR tail as cur_rand_decomp_fixed_rank (device: rsvd_b200_cur_from_id_dev) */
-void cur_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, mat **C, mat **U, mat **R) {
+static void cur_decomp_fixed_rank_or_prec_impl(mat *M, idx_t k, double TOL, idx_t *frank, mat **C, mat **U, mat **R) {
     idx_t m = M->nrows, n = M->ncols;
     vec *Icol = NULL, *Irow = NULL;
     mat *T = NULL, *S = NULL;
@@ -351,6 +371,11 @@ void cur_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, ma
     }
     vector_delete(Icol); vector_delete(Irow); matrix_delete(T); matrix_delete(S);
 }
+void cur_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *frank, mat **C, mat **U, mat **R) {   /* composite: nested calls keep one status */
+    rsvd_api_enter();
+    cur_decomp_fixed_rank_or_prec_impl(M, k, TOL, frank, C, U, R);
+    rsvd_api_leave();
+}
 
 void id_two_sided_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t q, idx_t s, vec **Icol, vec **Irow, mat **T, mat **S) {
     rsvd_api_begin();
@@ -361,16 +386,10 @@ void id_two_sided_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t q, idx_
         *Icol = vector_new(n); *Irow = vector_new(m); *T = matrix_new(max(k, 0), n - max(k, 0)); *S = matrix_new(max(k, 0), m - max(k, 0));
         return;
     }
-    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
-    double *dIc = rsvd_b200_dev_alloc(n + 1), *dIr = rsvd_b200_dev_alloc(m + 1);
-    double *dT = rsvd_b200_dev_alloc((rsvd_i64)k * (n - k) + 1), *dS = rsvd_b200_dev_alloc((rsvd_i64)k * (m - k) + 1);
-    if (dA && dIc && dIr && dT && dS)
-        rsvd_b200_id_two_sided_rand_dev(dA, m, n, m, k, p, (int)q, (int)s, omega_seed(), dIc, dIr, dT, k, dS, k);
-    rsvd_b200_dev_free(dA);
-    *Icol = download_vec(dIc, n); *Irow = download_vec(dIr, m);
-    *T = download_mat(dT, k, n - k); *S = download_mat(dS, k, m - k);
-    rsvd_b200_dev_free(dIc); rsvd_b200_dev_free(dIr); rsvd_b200_dev_free(dT); rsvd_b200_dev_free(dS);
+    *Icol = vector_new(n); *Irow = vector_new(m); *T = matrix_new(k, n - k); *S = matrix_new(k, m - k);
+    rsvd_b200_id_two_sided_rand_h(M->d, m, n, m, k, p, (int)q, (int)s, omega_seed(), (*Icol)->d, (*Irow)->d, (*T)->d, k, (*S)->d, k);
     rsvd_api_sync_error();
+    if (g_api_status) { zero_vec(*Icol); zero_vec(*Irow); zero_mat(*T); zero_mat(*S); }
 }
 
 void cur_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t q, idx_t s, mat **C, mat **U, mat **R) {
@@ -382,14 +401,10 @@ void cur_rand_decomp_fixed_rank(mat *M, idx_t k, idx_t p, idx_t q, idx_t s, mat 
         *C = matrix_new(m, max(k, 0)); *U = matrix_new(max(k, 0), max(k, 0)); *R = matrix_new(max(k, 0), n);
         return;
     }
-    double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
-    double *dC = rsvd_b200_dev_alloc((rsvd_i64)m * k + 1), *dU = rsvd_b200_dev_alloc((rsvd_i64)k * k + 1), *dR = rsvd_b200_dev_alloc((rsvd_i64)k * n + 1);
-    if (dA && dC && dU && dR)
-        rsvd_b200_cur_rand_dev(dA, m, n, m, k, p, (int)q, (int)s, omega_seed(), dC, m, dU, k, dR, k);
-    rsvd_b200_dev_free(dA);
-    *C = download_mat(dC, m, k); *U = download_mat(dU, k, k); *R = download_mat(dR, k, n);
-    rsvd_b200_dev_free(dC); rsvd_b200_dev_free(dU); rsvd_b200_dev_free(dR);
+    *C = rsvd_matrix_new_uninit(m, k); *U = matrix_new(k, k); *R = rsvd_matrix_new_uninit(k, n);
+    rsvd_b200_cur_rand_h(M->d, m, n, m, k, p, (int)q, (int)s, omega_seed(), (*C)->d, m, (*U)->d, k, (*R)->d, k);
     rsvd_api_sync_error();
+    if (g_api_status) { zero_mat(*C); zero_mat(*U); zero_mat(*R); }
 }
 
 /* ---- block-randomized ID / two-sided ID / CUR (RRA:1969-2027, 2086-2111, 2262-2332): consumers of the device QB ------------
@@ -403,11 +418,18 @@ static int blockrand_column_id(mat *M, idx_t k, idx_t p, double TOL, idx_t kstep
     if (!rankMode) nstep = 0;                                 /* RRA:1980-1983 */
     idx_t cap = 0, fr = 0;
     double *dA = NULL, *dQ = NULL, *dB = NULL;
+    void *qb = NULL;
     *dA_out = NULL; *dI_out = NULL; *dT_out = NULL;
-    if (randqb_device(M, kstep, nstep, TOL, q, s, &fr, &dA, &dQ, &dB, &cap)) {
-        rsvd_b200_dev_free(dA); rsvd_b200_dev_free(dQ); rsvd_b200_dev_free(dB);
+    /* these tails gather columns / rows of the ORIGINAL M on one device: keep the QB on the calling thread's GPU */
+    rsvd_b200_set_option("single_device", 1);
+    int bad = randqb_device(M, kstep, nstep, TOL, q, s, &fr, &qb, &cap);
+    rsvd_b200_set_option("single_device", 0);
+    if (bad || rsvd_b200_qb_dev_ptrs(qb, &dA, &dQ, &dB)) {
+        rsvd_b200_qb_free(qb);
+        rsvd_api_sync_error();
         return 1;
     }
+    rsvd_b200_qb_release_handle(qb);                       /* the three buffers are ours now */
     rsvd_b200_dev_free(dQ);
     idx_t rows = (nstep <= 0) ? fr : cap;                     /* B is cut to frank rows only in tolerance mode (RRA:1782-1789) */
     if (rankMode) *frank = k;                                 /* RRA:2001-2002 */
@@ -533,16 +555,21 @@ static void report(mat *M, mat *P, const char *what) {
     printf("percent_error between M and %s = %f\n", what, g_last_percent_error);
 }
 
-void use_QB_decomp_for_approximation(mat *M, mat *Q, mat *B) {
+static void use_QB_decomp_for_approximation_impl(mat *M, mat *Q, mat *B) {
     rsvd_api_begin();
     mat *P = matrix_new(M->nrows, M->ncols);
     matrix_matrix_mult(Q, B, P);
     report(M, P, "QB");
     matrix_delete(P);
 }
+void use_QB_decomp_for_approximation(mat *M, mat *Q, mat *B) {   /* composite: nested calls keep one status */
+    rsvd_api_enter();
+    use_QB_decomp_for_approximation_impl(M, Q, B);
+    rsvd_api_leave();
+}
 
 /* M ~ M(:,I(1:k)) [I_k T] P^T  (RRA:2402-2476) */
-void use_id_decomp_for_approximation(mat *M, mat *T, vec *I, idx_t k) {
+static void use_id_decomp_for_approximation_impl(mat *M, mat *T, vec *I, idx_t k) {
     rsvd_api_begin();
     idx_t m = M->nrows, n = M->ncols;
     mat *C = matrix_new(m, k), *CT = matrix_new(m, n - k), *P = matrix_new(m, n);
@@ -556,9 +583,14 @@ void use_id_decomp_for_approximation(mat *M, mat *T, vec *I, idx_t k) {
     report(M, P, "ID approximation");
     matrix_delete(C); matrix_delete(CT); matrix_delete(P);
 }
+void use_id_decomp_for_approximation(mat *M, mat *T, vec *I, idx_t k) {   /* composite: nested calls keep one status */
+    rsvd_api_enter();
+    use_id_decomp_for_approximation_impl(M, T, I, k);
+    rsvd_api_leave();
+}
 
 /* M ~ [I_k S]^T(Irow^{-1}) M(Irow(1:k), Icol(1:k)) [I_k T](Icol^{-1})  (RRA:2481-2558) */
-void use_id_two_sided_decomp_for_approximation(mat *M, mat *T, mat *S, vec *Icol, vec *Irow, idx_t k) {
+static void use_id_two_sided_decomp_for_approximation_impl(mat *M, mat *T, mat *S, vec *Icol, vec *Irow, idx_t k) {
     rsvd_api_begin();
     idx_t m = M->nrows, n = M->ncols;
     mat *Ms = matrix_new(k, k);
@@ -584,18 +616,28 @@ void use_id_two_sided_decomp_for_approximation(mat *M, mat *T, mat *S, vec *Icol
     report(M, P, "two sided ID approximation");
     matrix_delete(Ms); matrix_delete(MsT); matrix_delete(W); matrix_delete(StW); matrix_delete(P);
 }
+void use_id_two_sided_decomp_for_approximation(mat *M, mat *T, mat *S, vec *Icol, vec *Irow, idx_t k) {   /* composite: nested calls keep one status */
+    rsvd_api_enter();
+    use_id_two_sided_decomp_for_approximation_impl(M, T, S, Icol, Irow, k);
+    rsvd_api_leave();
+}
 
-void use_cur_decomp_for_approximation(mat *M, mat *C, mat *U, mat *R) {
+static void use_cur_decomp_for_approximation_impl(mat *M, mat *C, mat *U, mat *R) {
     rsvd_api_begin();
     mat *P = matrix_new(M->nrows, M->ncols);
     form_cur_product_matrix(C, U, R, P);
     report(M, P, "C U R");
     matrix_delete(P);
 }
+void use_cur_decomp_for_approximation(mat *M, mat *C, mat *U, mat *R) {   /* composite: nested calls keep one status */
+    rsvd_api_enter();
+    use_cur_decomp_for_approximation_impl(M, C, U, R);
+    rsvd_api_leave();
+}
 
 /* M(:, I) ~ Qk Rk  (RRA:2351-2384).  Deliberate deviation: the reference also frees the CALLER's Qk and Rk here (RRA:2378) and
  * its own driver 4 frees them again at exit (driver_multi_core_mkl4.c:139, a double free); the inputs are left alone. */
-void use_pivoted_QR_decomp_for_approximation(mat *M, mat *Qk, mat *Rk, vec *I) {
+static void use_pivoted_QR_decomp_for_approximation_impl(mat *M, mat *Qk, mat *Rk, vec *I) {
     rsvd_api_begin();
     idx_t m = M->nrows, n = M->ncols;
     mat *QR = matrix_new(m, n), *P = matrix_new(m, n);
@@ -604,6 +646,11 @@ void use_pivoted_QR_decomp_for_approximation(mat *M, mat *Qk, mat *Rk, vec *I) {
     g_last_percent_error = get_percent_error_between_two_mats(M, P);
     printf("percent_error between M and QkRkPt = %f\n", g_last_percent_error);
     matrix_delete(QR); matrix_delete(P);
+}
+void use_pivoted_QR_decomp_for_approximation(mat *M, mat *Qk, mat *Rk, vec *I) {   /* composite: nested calls keep one status */
+    rsvd_api_enter();
+    use_pivoted_QR_decomp_for_approximation_impl(M, Qk, Rk, I);
+    rsvd_api_leave();
 }
 
 /* ---- deterministic SVD baseline (RRA:7-69) ---------------------------------------------------------------------------
@@ -614,7 +661,7 @@ void low_rank_svd_decomp_fixed_rank_or_prec(mat *M, idx_t k, double TOL, idx_t *
     idx_t m = M->nrows, n = M->ncols, r = min(m, n);
     int tolMode = (k <= 0);
     if (tolMode) k = r;
-    if (k > r) { rsvd_api_error("low_rank_svd_decomp_fixed_rank_or_prec: k = %lld exceeds min(m,n) = %lld; clamped", (long long)k, (long long)r); k = r; }
+    if (k > r) { rsvd_api_warning("low_rank_svd_decomp_fixed_rank_or_prec: k = %lld exceeds min(m,n) = %lld; clamped", (long long)k, (long long)r); k = r; }
     double *dA = rsvd_upload(M->d, (size_t)m * (size_t)n);
     double *dU = rsvd_b200_dev_alloc((rsvd_i64)m * r + 1), *dS = rsvd_b200_dev_alloc(r + 1), *dV = rsvd_b200_dev_alloc((rsvd_i64)n * r + 1);
     if (dA && dU && dS && dV) rsvd_b200_svd_full_dev(dA, m, n, m, dU, m, dS, dV, n);
@@ -723,27 +770,42 @@ static void autorank_tail(mat *M, mat *Y, mat *Q, idx_t k, idx_t q, idx_t s, mat
     rsvd_api_sync_error();
 }
 /* RRA:701-759 */
-void randomized_low_rank_svd2_autorank1(mat *M, double frac_of_max_rank, double TOL, mat **U, mat **S, mat **V) {
+static void randomized_low_rank_svd2_autorank1_impl(mat *M, double frac_of_max_rank, double TOL, mat **U, mat **S, mat **V) {
     rsvd_api_begin();
     mat *Q = NULL; idx_t k = 0;
     estimate_rank_and_buildQ(M, frac_of_max_rank, TOL, &Q, &k);
     autorank_tail(M, NULL, Q, k, 1, 1, U, S, V);
     matrix_delete(Q);
 }
+void randomized_low_rank_svd2_autorank1(mat *M, double frac_of_max_rank, double TOL, mat **U, mat **S, mat **V) {   /* composite: nested calls keep one status */
+    rsvd_api_enter();
+    randomized_low_rank_svd2_autorank1_impl(M, frac_of_max_rank, TOL, U, S, V);
+    rsvd_api_leave();
+}
 /* RRA:763-822 */
-void randomized_low_rank_svd2_autorank2(mat *M, idx_t kblocksize, double TOL, mat **U, mat **S, mat **V) {
+static void randomized_low_rank_svd2_autorank2_impl(mat *M, idx_t kblocksize, double TOL, mat **U, mat **S, mat **V) {
     rsvd_api_begin();
     mat *Y = NULL, *Q = NULL; idx_t k = 0;
     estimate_rank_and_buildQ2(M, kblocksize, TOL, &Y, &Q, &k);
     autorank_tail(M, NULL, Q, k, 1, 1, U, S, V);
     matrix_delete(Y); matrix_delete(Q);
 }
+void randomized_low_rank_svd2_autorank2(mat *M, idx_t kblocksize, double TOL, mat **U, mat **S, mat **V) {   /* composite: nested calls keep one status */
+    rsvd_api_enter();
+    randomized_low_rank_svd2_autorank2_impl(M, kblocksize, TOL, U, S, V);
+    rsvd_api_leave();
+}
 /* RRA:826-918 */
-void randomized_low_rank_svd3_autorank2(mat *M, idx_t kblocksize, double TOL, idx_t q, idx_t s, mat **U, mat **S, mat **V) {
+static void randomized_low_rank_svd3_autorank2_impl(mat *M, idx_t kblocksize, double TOL, idx_t q, idx_t s, mat **U, mat **S, mat **V) {
     rsvd_api_begin();
     mat *Y = NULL, *Q = NULL; idx_t k = 0;
     if (s <= 0) { rsvd_api_error("randomized_low_rank_svd3_autorank2: need s > 0"); }
     estimate_rank_and_buildQ2(M, kblocksize, TOL, &Y, &Q, &k);
     autorank_tail(M, Y, Q, k, q, s, U, S, V);
     matrix_delete(Y); matrix_delete(Q);
+}
+void randomized_low_rank_svd3_autorank2(mat *M, idx_t kblocksize, double TOL, idx_t q, idx_t s, mat **U, mat **S, mat **V) {   /* composite: nested calls keep one status */
+    rsvd_api_enter();
+    randomized_low_rank_svd3_autorank2_impl(M, kblocksize, TOL, q, s, U, S, V);
+    rsvd_api_leave();
 }

@@ -65,6 +65,22 @@ SIGNATURES = {
     "rsvd_b200_svd_from_qb_dev": (C.c_int, [dp, i64, i64, dp, i64, i64, i64, dp, i64, dp, dp, i64]),
     "rsvd_b200_id_two_sided_rand_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, dp, dp, dp, i64, dp, i64]),
     "rsvd_b200_cur_rand_dev": (C.c_int, [dp, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, dp, i64, dp, i64, dp, i64]),
+    "rsvd_b200_svd_rand_h": (C.c_int, [C.c_void_p, i64, i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, u64, C.c_void_p, i64, C.c_void_p, C.c_void_p, i64]),
+    "rsvd_b200_id_rand_h": (C.c_int, [C.c_void_p, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, C.c_void_p, C.c_void_p, i64]),
+    "rsvd_b200_id_two_sided_rand_h": (C.c_int, [C.c_void_p, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, C.c_void_p, C.c_void_p, C.c_void_p, i64, C.c_void_p, i64]),
+    "rsvd_b200_cur_rand_h": (C.c_int, [C.c_void_p, i64, i64, i64, i64, i64, C.c_int, C.c_int, u64, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64]),
+    "rsvd_b200_randqb_h": (C.c_void_p, [C.c_void_p, i64, i64, i64, i64, i64, i64, C.c_double, C.c_int, C.c_int, u64, C.POINTER(i64)]),
+    "rsvd_b200_qb_parts": (i64, [C.c_void_p]),
+    "rsvd_b200_qb_download": (C.c_int, [C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64]),
+    "rsvd_b200_qb_svd": (C.c_int, [C.c_void_p, i64, i64, C.c_int, C.c_void_p, i64, C.c_void_p, C.c_void_p, i64]),
+    "rsvd_b200_qb_dev_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "rsvd_b200_qb_release_handle": (None, [C.c_void_p]),
+    "rsvd_b200_qb_free": (None, [C.c_void_p]),
+    "rsvd_b200_pin_matrix": (C.c_int, [C.c_void_p, i64, i64]),
+    "rsvd_b200_unpin_matrix": (None, [C.c_void_p]),
+    "rsvd_b200_is_resident": (C.c_int, [C.c_void_p]),
+    "rsvd_b200_set_devices": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "rsvd_b200_active_devices": (C.c_int, []),
     "rsvd_b200_jacobi_schedule": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "rsvd_b200_load_binary_dev": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(i64)]),
     "rsvd_b200_store_binary_dev": (C.c_int, [C.c_char_p, C.c_int, dp, i64, i64, i64]),

@@ -4,8 +4,10 @@ import numpy as np
 
 def subspace_sin(U, V):
     """sin of the largest principal angle between span(U) and span(V) (orthonormal columns)."""
-    s = np.linalg.svd(U.T @ V, compute_uv=False)
-    return float(np.sqrt(max(0.0, 1.0 - min(s.min(), 1.0) ** 2)))
+    if U.shape[1] != V.shape[1]:
+        s = np.linalg.svd(U.T @ V, compute_uv=False)
+        return float(np.sqrt(max(0.0, 1.0 - min(s.min(), 1.0) ** 2)))
+    return float(np.linalg.norm(V - U @ (U.T @ V), 2))     # ||(I - U U^T) V||_2: accurate for small angles
 
 
 def col_alignment(U, V):

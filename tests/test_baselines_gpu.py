@@ -379,7 +379,8 @@ def test_invalid_parameters_are_reported_not_fatal(api):
         call()                                                           # returns (void API), outputs allocated
         with pytest.raises(RuntimeError):
             api.check()
-    f, Q, R, I = api.pqr(A, 99, 0.0)                                     # k > min(m,n): clamped, reported
-    assert f <= 15
-    with pytest.raises(RuntimeError):
-        api.check()
+    f, Q, R, I = api.pqr(A, 99, 0.0)                                     # k > min(m,n): clamped — a warning, not an error:
+    assert f <= 15 and np.abs(R).max() > 0 and np.abs(Q).max() > 0       # every output carries the (clamped) result
+    api.check()
+    api.lib.rsvd_b200_api_last_warning.restype = __import__("ctypes").c_char_p
+    assert b"clamped" in api.lib.rsvd_b200_api_last_warning()
