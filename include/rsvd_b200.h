@@ -35,7 +35,7 @@ void *rsvd_b200_stream(void);                   /* the cudaStream_t all kernels 
 void rsvd_b200_sync(void);
 unsigned long long rsvd_b200_launch_count(void); /* kernels launched by this library so far */
 /* options: "seed" (Omega seed, default 777 = the reference's unused `#define SEED 777`, MVH:10),
- * "verbose", "force_generic_gemm", "force_qr_fallback", "single_device" (host-level calls ignore the worker pool);
+ * "verbose", "force_generic_gemm", "force_qr_fallback", "force_unblocked_qr", "single_device" (host-level calls ignore the worker pool);
  * in a process-per-GPU job "row0" / "m_global" place this rank's row block in the global matrix */
 void rsvd_b200_set_option(const char *name, rsvd_i64 value);
 rsvd_i64 rsvd_b200_get_option(const char *name); /* also "last_gemm_path", "last_qr_path", "qr_fallbacks", "sms" */
@@ -63,6 +63,8 @@ int rsvd_b200_fill_normal(double *d, rsvd_i64 n, uint64_t seed, rsvd_i64 first);
 int rsvd_b200_orthonormalize(double *Y, rsvd_i64 ldy, rsvd_i64 m, rsvd_i64 l, double *R, rsvd_i64 ldr);
 /* pivotedQR_mkl (RRA:924-976; dgeqp3): in place, R in the upper triangle, jpvt 0-based stored as doubles. */
 int rsvd_b200_geqp3(double *A, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n, double *jpvt);
+/* the same followed by dorgqr (RRA:957-964): Q (m x min(m,n)) is formed from the Householder reflectors, orthonormal for any input */
+int rsvd_b200_geqp3_q(double *A, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n, double *jpvt, double *Q, rsvd_i64 ldq);
 /* singular_value_decomposition (MVF:1270-1284; dgesvd 'S','S') for square n x n: A = U diag(s) Vt, s descending. */
 int rsvd_b200_svd_small(double *A, rsvd_i64 lda, rsvd_i64 n, double *U, rsvd_i64 ldu, double *s, double *Vt, rsvd_i64 ldvt);
 /* compute_evals_and_evecs_of_symm_matrix (MVF:1206-1209; dsyev 'V','U'): ascending w, vectors overwrite A. */

@@ -65,6 +65,12 @@ int rsvd_b200_geqp3(double *A, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n, double *jpv
     return g_status;
 }
 
+int rsvd_b200_geqp3_q(double *A, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n, double *jpvt, double *Q, rsvd_i64 ldq) {
+    READY();
+    geqp3_q(A, lda, m, n, jpvt, Q, ldq);
+    return finish(g_status);
+}
+
 int rsvd_b200_svd_small(double *A, rsvd_i64 lda, rsvd_i64 n, double *U, rsvd_i64 ldu, double *s, double *Vt, rsvd_i64 ldvt) {
     READY();
     jacobi_svd(A, lda, n, U, ldu, s, Vt, ldvt);

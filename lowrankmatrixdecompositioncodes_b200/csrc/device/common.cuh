@@ -47,6 +47,10 @@ struct Ctx {
     int verbose = 0;
     int force_generic_gemm = 0;
     int force_qr_fallback = 0;
+    int sketch_int_widen = 0;        // experiment: widen the generated float32 normals to double with integer ops (no F2F on the FP64 pipe)
+    int no_sketch_cluster = 0;       // option: sketch kernel without 2-CTA clusters (each CTA generates its own Omega stages)
+    int qr_blocked_rows = 2048;      // inputs with at most this many rows go to the blocked pivoted QR (geqp3_blocked.cu)
+    int force_unblocked_qr = 0;      // option: pivoted QR through the one-reflector-per-step kernel even for short-wide inputs
     int jacobi_transpose = 0;        // run the one-sided Jacobi on R^T (lower triangular) instead of R
     void *staging = nullptr;         // pinned staging buffers of this context (runtime.cu)
     int last_qr_path = 0;            // 1 = CholeskyQR2, 2 = TSQR-preconditioned fallback, 3 = Householder with explicit Q (singular panel)
@@ -149,6 +153,15 @@ void trtri_upper(const double *R, i64 ldr, i64 n, double *Rinv, i64 ldi); // Rin
 // ---- Householder QR family (geqp3.cu) ----------------------------------------------------------
 // In-place dgeqp3-compatible column-pivoted QR (R in the upper triangle, jpvt 0-based as doubles).
 void geqp3(double *A, i64 lda, i64 m, i64 n, double *jpvt_out);
+// geqp3_blocked.cu: dlaqps-style blocked kernel for rows <= 4096 (classic in-place layout; tau_out optional)
+bool geqp3_blocked_ok(i64 m, i64 n);
+void geqp3_blocked(double *A, i64 lda, i64 m, i64 n, double *jpvt_out, double *tau_out);
+// pivoted QR + T = R11(0:k,0:k)^{-1} R(0:k, k:n) of an r x n_global matrix given by this rank's columns [col0, col0+nloc)
+// (Y destroyed; `per` = columns per rank of the regular sharding; sharded == false: this rank holds all columns, no communication).
+// I (n_global) and T (k x (n_global-k)) are produced on every rank.
+void geqp3_id(double *Y, i64 ldy, i64 r, i64 nloc, i64 col0, i64 n_global, i64 per, bool sharded, i64 k, double *I, double *T, i64 ldt);
+// dgeqp3 + dorgqr: A <- R (upper triangle/trapezoid), jpvt, and the explicit thin Q (m x min(m,n)) from the reflectors
+void geqp3_q(double *A, i64 lda, i64 m, i64 n, double *jpvt_out, double *Q, i64 ldq);
 // unpivoted Householder, R only (upper triangle of A on exit), used by the TSQR fallback
 void geqrf_r(double *A, i64 lda, i64 m, i64 n);
 // dgeqrf + dorgqr (m >= n): A <- explicit thin Q (LAPACK sign convention), R (n x n upper, optional) — any rank

@@ -37,6 +37,13 @@ extern template bool launch_tma<13>(bool, bool, const CUtensorMap &, const CUten
 extern template bool launch_tma<14>(bool, bool, const CUtensorMap &, const CUtensorMap &, const TmaP &, unsigned);
 extern template bool launch_tma<15>(bool, bool, const CUtensorMap &, const CUtensorMap &, const TmaP &, unsigned);
 extern template bool launch_tma<16>(bool, bool, const CUtensorMap &, const CUtensorMap &, const TmaP &, unsigned);
+extern template int max_sketch_clusters<4>(bool);
+extern template int max_sketch_clusters<8>(bool);
+extern template int max_sketch_clusters<12>(bool);
+extern template int max_sketch_clusters<13>(bool);
+extern template int max_sketch_clusters<14>(bool);
+extern template int max_sketch_clusters<15>(bool);
+extern template int max_sketch_clusters<16>(bool);
 }
 
 namespace {
@@ -72,6 +79,27 @@ bool make_map(CUtensorMap *map, const double *base, i64 inner, i64 outer, i64 ld
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
+}
+
+// co-resident sketch clusters for this tile width on the current device (queried once per device / width / layout)
+int sketch_cluster_slots(int nb_tile, bool ta) {
+    static int cache[16][17][2];       // [device][nb][ta], 0 = not asked yet, -1 = unavailable
+    const int dev = ctx().device & 15;
+    int &c = cache[dev][nb_tile][ta ? 1 : 0];
+    if (c == 0) {
+        int n = 0;
+        switch (nb_tile) {
+            case 4: n = max_sketch_clusters<4>(ta); break;
+            case 8: n = max_sketch_clusters<8>(ta); break;
+            case 12: n = max_sketch_clusters<12>(ta); break;
+            case 13: n = max_sketch_clusters<13>(ta); break;
+            case 14: n = max_sketch_clusters<14>(ta); break;
+            case 15: n = max_sketch_clusters<15>(ta); break;
+            case 16: n = max_sketch_clusters<16>(ta); break;
+        }
+        c = n > 0 ? n : -1;
+    }
+    return c > 0 ? c : 0;
 }
 
 }  // namespace
@@ -111,6 +139,13 @@ bool gemm_tma_try(const Gemm &g) {
     p.c_vec2 = (((uintptr_t)g.C & 15) == 0 && (g.ldc & 1) == 0) ? 1 : 0;
     const i64 tm = (g.m + BM - 1) / BM;
     i64 tiles = tm * T;
+    // sketch: clusters of two row tiles share every generated Omega stage (work units are then PAIRS of row tiles)
+    int slots = ctx().sms;
+    p.cl = 0;
+    if (g.philox && tm >= 2 && !ctx().no_sketch_cluster) {
+        const int cs = sketch_cluster_slots(nb_tile, ta);
+        if (cs >= 8) { p.cl = ctx().sketch_int_widen ? 2 : 1; slots = cs; tiles = ((tm + 1) / 2) * T; }
+    }
     p.b_upper = (g.b_upper && !g.philox) ? 1 : 0;
     p.sym = 0;
     if (g.sym_upper && g.m == g.n && !g.philox) {           // only the tiles meeting the upper triangle
@@ -121,7 +156,7 @@ bool gemm_tma_try(const Gemm &g) {
     if (tiles > 0x3fffffffll) return false;
     p.tiles_n = (int)T; p.nb_tile = nb_tile;
     p.total_iters = (int)((g.k + BK - 1) / BK);
-    const int sms = ctx().sms;
+    const int sms = slots;              // schedulable units per wave: SMs, or co-resident clusters
     int max_split = max(1, min(16, p.total_iters / 32));   // keep >= 32 k-iterations per unit
     if (g.sumsq_out) max_split = 1;                        // the fused norm lives in the direct-store epilogue
     p.main_tiles = (int)tiles; p.s_main = 1; p.s_tail = 1;
@@ -146,27 +181,32 @@ bool gemm_tma_try(const Gemm &g) {
         // partial tiles are indexed by unit id; when only the tail is split the main units do not touch the buffer,
         // so shift the base instead of allocating their slots
         const i64 first_split_unit = (p.s_main > 1) ? 0 : (i64)p.main_tiles * p.s_main;
-        part.alloc((size_t)(units - first_split_unit) * PART_TILE);
-        p.part = part.p - first_split_unit * PART_TILE;
+        const i64 per_unit = p.cl ? 2 : 1;           // a cluster unit writes one partial tile per member CTA
+        part.alloc((size_t)((units - first_split_unit) * per_unit) * PART_TILE);
+        p.part = part.p - first_split_unit * per_unit * PART_TILE;
     }
     DBuf ss_part;
     p.ss_part = nullptr;
     if (g.sumsq_out) { ss_part.alloc((size_t)units * 8); p.ss_part = ss_part.p; }
+    const unsigned grid = (unsigned)(p.cl ? 2 * units : units);
+    if (g.philox && ctx().verbose >= 2)
+        fprintf(stderr, "[rsvd_b200] sketch %lld x %lld x %lld: %s, %d slots per wave, %lld units (%d main tiles x %d, tail x %d), tile width %d\n", (long long)g.m, (long long)g.n,
+                (long long)g.k, p.cl ? "2-CTA clusters" : "single CTAs", slots, (long long)units, p.main_tiles, p.s_main, p.s_tail, 8 * nb_tile);
     bool launched = false;
     switch (nb_tile) {
-        case 4: launched = launch_tma<4>(ta, g.philox, mapA, mapB, p, (unsigned)units); break;
-        case 8: launched = launch_tma<8>(ta, g.philox, mapA, mapB, p, (unsigned)units); break;
-        case 12: launched = launch_tma<12>(ta, g.philox, mapA, mapB, p, (unsigned)units); break;
-        case 13: launched = launch_tma<13>(ta, g.philox, mapA, mapB, p, (unsigned)units); break;
-        case 14: launched = launch_tma<14>(ta, g.philox, mapA, mapB, p, (unsigned)units); break;
-        case 15: launched = launch_tma<15>(ta, g.philox, mapA, mapB, p, (unsigned)units); break;
-        case 16: launched = launch_tma<16>(ta, g.philox, mapA, mapB, p, (unsigned)units); break;
+        case 4: launched = launch_tma<4>(ta, g.philox, mapA, mapB, p, grid); break;
+        case 8: launched = launch_tma<8>(ta, g.philox, mapA, mapB, p, grid); break;
+        case 12: launched = launch_tma<12>(ta, g.philox, mapA, mapB, p, grid); break;
+        case 13: launched = launch_tma<13>(ta, g.philox, mapA, mapB, p, grid); break;
+        case 14: launched = launch_tma<14>(ta, g.philox, mapA, mapB, p, grid); break;
+        case 15: launched = launch_tma<15>(ta, g.philox, mapA, mapB, p, grid); break;
+        case 16: launched = launch_tma<16>(ta, g.philox, mapA, mapB, p, grid); break;
         default: return false;
     }
     if (!launched) return false;
     const i64 split_tiles = (p.s_main > 1 ? p.main_tiles : 0) + (p.s_tail > 1 ? tail_tiles : 0);
     if (split_tiles > 0) {
-        tile_reduce_kernel<<<(unsigned)split_tiles, 256, 0, ctx().stream>>>(p, 0);
+        tile_reduce_kernel<<<(unsigned)(p.cl ? 2 * split_tiles : split_tiles), 256, 0, ctx().stream>>>(p, 0);
         count_launch();
     }
     if (g.sumsq_out) sum_array_async(ss_part.p, units * 8, g.sumsq_out);

@@ -28,6 +28,7 @@ struct TmaP {
     int sym;              // C is symmetric and only its upper triangle is wanted: tiles entirely below the diagonal are skipped
     int b_upper;          // op(B) (k x n) is upper triangular: column tile [n0, n0+w) only needs k < n0 + w
     uint64_t seed; i64 ph_sk, ph_sc, ph_off;
+    int cl;               // sketch kernel launched as clusters of 2 CTAs (same column tile, adjacent row tiles) sharing the generated Omega
     double *ss_part;      // non-null: consumer warp w of unit u also writes the sum of squares of the C entries it stored to ss_part[8u + w]
 };
 
@@ -91,6 +92,50 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// ---- cluster (DSMEM) helpers: the two CTAs of a sketch cluster write each other's Omega stage and signal each other's barriers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_peer(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+// asynchronous DSMEM stores (STAS): the data lands in the peer CTA's shared memory and completes 16 / 8 bytes of the peer's
+// transaction barrier — the same mechanism a TMA load uses, so the consumer needs neither a per-thread arrive nor a cluster fence
+__device__ __forceinline__ void stas128(uint32_t addr, double x, double y, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(addr), "d"(x), "d"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void stas64(uint32_t addr, double x, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(addr), "d"(x), "r"(bar) : "memory");
+}
+// "this warp is done READING the stage": nothing has to be published, and the reads have completed (their values fed the
+// DMMAs already issued), so the remote arrive is relaxed — a release at cluster scope costs a MEMBAR.ALL.GPU per stage and warp
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITC_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEC_%=;\n"
+        "bra WAITC_%=;\n"
+        "DONEC_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// float -> double widening without the FP64 pipe (F2F.F64.F32 shares it with the consumers' DMMAs): exact for zeros and normal
+// floats — the only values Box-Muller on (0,1] uniforms produces besides (never reached) subnormals, which flush to signed zero
+__device__ __forceinline__ double widen_int(float f) {
+    const uint32_t u = __float_as_uint(f);
+    const uint32_t mag = u & 0x7fffffffu;
+    uint32_t hi = (mag >> 3) + 0x38000000u;                 // exponent rebias 127 -> 1023, top 20 mantissa bits
+    if (mag < 0x00800000u) hi = 0u;                          // zero (and subnormal) -> zero
+    return __hiloint2double((int)(hi | (u & 0x80000000u)), (int)(mag < 0x00800000u ? 0u : (u << 29)));
+}
+template <bool INTW> __device__ __forceinline__ double widen(float f) { return INTW ? widen_int(f) : (double)f; }
+
 // byte offset of element (column j, k index kk) inside a K-major [col][16 k] stage under SWIZZLE_128B
 __device__ __forceinline__ uint32_t bswz(int j, int kk) {
     return (uint32_t)(j * 128 + ((((kk >> 1) ^ (j & 7))) << 4) + (kk & 1) * 8);
@@ -104,9 +149,15 @@ __device__ __forceinline__ void decode_unit(const TmaP &p, int unit, int &tile, 
 }
 
 // A_KMAJOR: op(A) = A^T with A stored k x m (TN); otherwise A stored m x k (NN).  PHILOX: B generated on the fly.
-template <bool A_KMAJOR, bool PHILOX, int NB>
+// CL (sketch only): clusters of two CTAs working on the same column tile and adjacent row tiles.  Every Omega stage is
+// generated ONCE per cluster — each CTA produces the half of the k-range given by its cluster rank, stores it into its own
+// shared memory and ships it to the peer with asynchronous DSMEM stores that complete the peer's transaction barrier — so the
+// Philox + Box-Muller work per CTA halves.  full = expect_tx arrive + one elected lane per generator warp; empty counts the
+// consumer warps of both CTAs.
+template <bool A_KMAJOR, bool PHILOX, int NB, bool CL = false>
 __global__ void __launch_bounds__(PHILOX ? NTHREADS_PHILOX : NTHREADS, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TmaP p) {
+    static_assert(!CL || PHILOX, "clusters are only used by the sketch kernel");
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = smem_base;
@@ -118,9 +169,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     int tile, split, nsplit;
-    decode_unit(p, (int)blockIdx.x, tile, split, nsplit);
+    const uint32_t crank = CL ? cluster_ctarank() : 0u;
+    decode_unit(p, CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile, split, nsplit);
     int tile_n, tile_m;
-    tile_to_mn(p, tile, tile_m, tile_n);
+    if (CL) { tile_n = tile % p.tiles_n; tile_m = 2 * (tile / p.tiles_n) + (int)crank; }   // a row tile past the matrix computes zeros and stores nothing
+    else tile_to_mn(p, tile, tile_m, tile_n);
     const i64 m0 = (i64)tile_m * BM, n0 = (i64)tile_n * (8 * NB);
     // NB = column groups per n-tile (compile time).  Columns beyond n in the last tile are zero-filled by TMA (or
     // generated and never stored), so every tile runs the same branch-free inner loop.
@@ -132,12 +185,14 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), PHILOX ? 129 : 1);
-            mbar_init(empty_bar(s), 8);
+            mbar_init(full_bar(s), PHILOX ? (CL ? 5 : 129) : 1);     // expect_tx arrive + the generator threads (CL: one lane per generator warp)
+            mbar_init(empty_bar(s), CL ? 16 : 8);                    // the consumer warps (of both CTAs)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (CL) cluster_sync_all();            // the peer's barriers exist before anything is signalled remotely
+    const uint32_t peer = crank ^ 1u;
 
     constexpr int NPWG = PHILOX ? 2 : 1;     // producer warpgroups
     if (warp < 4 * NPWG) {
@@ -156,7 +211,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const int kc = (it0 + it) * BK;
                 if (ptid == 0) {
                     const uint32_t fb = full_bar(s);
-                    mbar_expect_tx(fb, PHILOX ? A_STAGE_BYTES : (A_STAGE_BYTES + b_bytes));
+                    mbar_expect_tx(fb, PHILOX ? (CL ? A_STAGE_BYTES + b_bytes / 2 : A_STAGE_BYTES) : (A_STAGE_BYTES + b_bytes));   // CL: + the peer's half of Omega
                     if (A_KMAJOR) {
                         tma_load_2d(sA + s * A_STAGE_BYTES, &mapA, kc, (int)m0, fb);
                     } else {
@@ -171,6 +226,66 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     // (the image a TMA SWIZZLE_128B load of a stored Omega would have produced).
                     const uint32_t bbase = sB + s * B_STAGE_BYTES;
                     constexpr int ncols = 8 * NB;
+                    if (CL) {
+                        // this CTA's half of the stage: k in [8*crank, 8*crank + 8), written to both CTAs of the cluster
+                        const uint32_t rbase = mapa_peer(bbase, peer), rbar = mapa_peer(full_bar(s), peer);
+                        const int k0h = 8 * (int)crank;
+                        if (p.ph_sk == 1) {
+                            const int j = ptid;
+                            if (j < ncols) {
+                                const uint64_t lin0 = (uint64_t)(p.ph_off + (i64)kc + k0h + (n0 + j) * p.ph_sc);
+                                if ((lin0 & 3u) == 0) {
+                                    float z[2][4];
+#pragma unroll
+                                    for (int qd = 0; qd < 2; ++qd) rsvd_normal4(p.seed, (lin0 >> 2) + qd, z[qd]);
+#pragma unroll
+                                    for (int qd = 0; qd < 2; ++qd) {
+                                        const int ch = 4 * (int)crank + 2 * qd;       // 16-byte chunk index of k = k0h + 4 qd
+                                        const uint32_t o0 = (uint32_t)(j * 128 + ((ch ^ (j & 7)) << 4)), o1 = (uint32_t)(j * 128 + (((ch + 1) ^ (j & 7)) << 4));
+                                        double a0, a1, a2, a3;
+                                        if (p.cl == 2) { a0 = widen_int(z[qd][0]); a1 = widen_int(z[qd][1]); a2 = widen_int(z[qd][2]); a3 = widen_int(z[qd][3]); }
+                                        else { a0 = (double)z[qd][0]; a1 = (double)z[qd][1]; a2 = (double)z[qd][2]; a3 = (double)z[qd][3]; }
+                                        sts128(bbase + o0, a0, a1); sts128(bbase + o1, a2, a3);
+                                        stas128(rbase + o0, a0, a1, rbar); stas128(rbase + o1, a2, a3, rbar);
+                                    }
+                                } else {
+                                    uint64_t cached = ~0ull;
+                                    float z[4];
+                                    for (int kk = k0h; kk < k0h + 8; ++kk) {
+                                        const uint64_t lin = lin0 + (uint64_t)(kk - k0h);
+                                        if ((lin >> 2) != cached) { cached = lin >> 2; rsvd_normal4(p.seed, cached, z); }
+                                        const uint32_t sel = (uint32_t)lin & 3u;
+                                        const double f = (double)(sel == 0 ? z[0] : (sel == 1 ? z[1] : (sel == 2 ? z[2] : z[3])));
+                                        sts64(bbase + bswz(j, kk), f); stas64(rbase + bswz(j, kk), f, rbar);
+                                    }
+                                }
+                            }
+                        } else if (p.ph_sc == 1 && ((p.ph_sk | (p.ph_off + n0)) & 3) == 0) {
+                            constexpr int nitems = 8 * 2 * NB;     // 8 k  x  ncols/4 quads
+#pragma unroll
+                            for (int r = 0; r < 2; ++r) {
+                                const int item = ptid + r * 128;
+                                if (item < nitems) {
+                                    const int kk = k0h + (item & 7), cq = item >> 3;
+                                    const uint64_t lin = (uint64_t)(p.ph_off + ((i64)kc + kk) * p.ph_sk + n0 + 4 * cq);
+                                    float z[4];
+                                    rsvd_normal4(p.seed, lin >> 2, z);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) { const uint32_t o = bswz(4 * cq + i, kk); sts64(bbase + o, (double)z[i]); stas64(rbase + o, (double)z[i], rbar); }
+                                }
+                            }
+                        } else {
+                            for (int e = ptid; e < ncols * 8; e += 128) {
+                                const int kk = k0h + (e & 7), j = e >> 3;
+                                const uint64_t lin = (uint64_t)(p.ph_off + ((i64)kc + kk) * p.ph_sk + (n0 + j) * p.ph_sc);
+                                const double f = (double)rsvd_normal_at(p.seed, lin);
+                                sts64(bbase + bswz(j, kk), f); stas64(rbase + bswz(j, kk), f, rbar);
+                            }
+                        }
+                        __syncwarp();
+                        if ((ptid & 31) == 0) mbar_arrive(full_bar(s));      // publishes this warp's local half (release, CTA scope)
+                        continue;
+                    }
                     if (p.ph_sk == 1) {
                         // linear index runs along k: thread = column, its 16 entries are 4 aligned Philox blocks
                         const int j = ptid;
@@ -294,7 +409,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty_bar(s));
+            if (lane == 0) {
+                mbar_arrive(empty_bar(s));
+                if (CL) mbar_arrive_remote_relaxed(mapa_peer(empty_bar(s), peer));
+            }
         }
 
         // ---- epilogue: accumulators -> C, or the unit's partial tile ----
@@ -361,27 +479,33 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     }
+    if (CL) cluster_sync_all();            // neither CTA leaves while the other may still signal its barriers
 }
 
 // sums the partial tiles of split units in fixed order: C = alpha * sum_s P[s] + beta * C.  One CTA per split tile.
 static __global__ void __launch_bounds__(256) tile_reduce_kernel(TmaP p, int first_split_tile_is_main) {
-    // split tiles: if s_main > 1 all main tiles (index 0..main_tiles-1) come first, then the tail tiles
-    int st = blockIdx.x, tile, nsplit, unit0;
+    // split tiles: if s_main > 1 all main tiles (index 0..main_tiles-1) come first, then the tail tiles.
+    // Cluster launches (p.cl): "tile" is a PAIR of row tiles; CTA 2u + r of unit u holds the partial of row tile 2*(tile / tiles_n) + r.
+    const int member = p.cl ? (int)(blockIdx.x & 1) : 0;
+    int st = p.cl ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile, nsplit, unit0;
     const int n_main_split = (p.s_main > 1) ? p.main_tiles : 0;
     if (st < n_main_split) { tile = st; nsplit = p.s_main; unit0 = tile * p.s_main; }
     else { int tt = st - n_main_split; tile = p.main_tiles + tt; nsplit = p.s_tail; unit0 = p.main_tiles * p.s_main + tt * p.s_tail; }
     (void)first_split_tile_is_main;
     int tile_n, tile_m;
-    tile_to_mn(p, tile, tile_m, tile_n);
+    if (p.cl) { tile_n = tile % p.tiles_n; tile_m = 2 * (tile / p.tiles_n) + member; }
+    else tile_to_mn(p, tile, tile_m, tile_n);
     const i64 m0 = (i64)tile_m * BM, n0 = (i64)tile_n * (8 * p.nb_tile);
+    if (m0 >= p.m) return;
     const int ncols = (int)min((i64)(8 * p.nb_tile), p.n - n0);
-    const double *P = p.part + (i64)unit0 * PART_TILE;
+    const i64 pstride = p.cl ? 2 * (i64)PART_TILE : (i64)PART_TILE;
+    const double *P = p.part + (p.cl ? ((i64)unit0 * 2 + member) : (i64)unit0) * PART_TILE;
     for (int e = threadIdx.x; e < ncols * BM; e += blockDim.x) {
         const int r = e % BM, c = e / BM;
         const i64 row = m0 + r, col = n0 + c;
         if (row >= p.m) continue;
         double s = 0.0;
-        for (int u = 0; u < nsplit; ++u) s += P[(i64)u * PART_TILE + c * BM + r];
+        for (int u = 0; u < nsplit; ++u) s += P[(i64)u * pstride + c * BM + r];
         double *dst = p.C + col * p.ldc + row;
         double v = p.alpha * s;
         if (p.beta != 0.0) v += p.beta * (*dst);
@@ -396,12 +520,41 @@ bool launch_tma(bool a_kmajor, bool philox, const CUtensorMap &ma, const CUtenso
     auto go = [&](auto kern) -> bool {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        if (p.cl) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(philox ? NTHREADS_PHILOX : NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = ctx().stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, kern, ma, mb, p);
+            count_launch();
+            if (e != cudaSuccess) { (void)cudaGetLastError(); return false; }
+            return true;
+        }
         kern<<<grid, philox ? NTHREADS_PHILOX : NTHREADS, SMEM_BYTES, ctx().stream>>>(ma, mb, p);
         count_launch();
         return cudaGetLastError() == cudaSuccess;
     };
+    if (p.cl) return a_kmajor ? go(gemm_tma_kernel<true, true, NB, true>) : go(gemm_tma_kernel<false, true, NB, true>);
     if (a_kmajor) return philox ? go(gemm_tma_kernel<true, true, NB>) : go(gemm_tma_kernel<true, false, NB>);
     return philox ? go(gemm_tma_kernel<false, true, NB>) : go(gemm_tma_kernel<false, false, NB>);
+}
+
+// co-resident 2-CTA clusters of the sketch kernel on this device (0: cluster launch not possible)
+template <int NB>
+int max_sketch_clusters(bool a_kmajor) {
+    auto q = [&](auto kern) -> int {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * 148); cfg.blockDim = dim3(NTHREADS_PHILOX); cfg.dynamicSmemBytes = SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+        return n;
+    };
+    return a_kmajor ? q(gemm_tma_kernel<true, true, NB, true>) : q(gemm_tma_kernel<false, true, NB, true>);
 }
 
 }  // namespace tma

@@ -19,38 +19,11 @@
 // Structure: per Householder step one single-CTA kernel (pivot search, column swap, reflector) and one wide
 // kernel applying H_i to all trailing columns and downdating their norms (each column is read and written once).
 #include "common.cuh"
+#include "ddsum.cuh"
 
 namespace rsvd {
 
 namespace {
-
-struct dd { double hi, lo; };
-__device__ __forceinline__ dd dd_add_sq(dd a, double x) {   // a += x*x, error-free product + two-sum
-    double p = x * x;
-    double e = fma(x, x, -p);
-    double s = a.hi + p;
-    double bb = s - a.hi;
-    double err = (a.hi - (s - bb)) + (p - bb);
-    a.hi = s; a.lo += err + e;
-    return a;
-}
-__device__ __forceinline__ dd dd_add(dd a, dd b) {
-    double s = a.hi + b.hi;
-    double bb = s - a.hi;
-    double err = (a.hi - (s - bb)) + (b.hi - bb);
-    dd r; r.hi = s; r.lo = a.lo + b.lo + err;
-    return r;
-}
-__device__ __forceinline__ dd dd_warp_sum(dd a) {
-    for (int o = 16; o > 0; o >>= 1) {
-        dd b;
-        b.hi = __shfl_xor_sync(0xffffffffu, a.hi, o);
-        b.lo = __shfl_xor_sync(0xffffffffu, a.lo, o);
-        a = dd_add(a, b);
-    }
-    return a;
-}
-__device__ __forceinline__ double dd_sqrt(dd a) { return sqrt(a.hi + a.lo); }
 
 // block-wide dd sum; result valid in all threads. sh must hold 2*32 doubles.
 __device__ double block_nrm2(dd a, double *sh) {
@@ -364,7 +337,7 @@ struct RefOpts { int tolmode; double tol; int zero_exact; i64 frank; double *Q; 
 
 // qr_out (pivoting == 0 only): after the factorisation A is replaced by the explicit thin Q and R (n x n upper) goes to Rq.
 void householder_qr(double *A, i64 lda, i64 m, i64 n, int pivoting, double *jpvt_out, i64 steps = -1, RefOpts *ro = nullptr,
-                    bool q_out = false, double *Rq = nullptr, i64 ldrq = 0) {
+                    bool q_out = false, double *Rq = nullptr, i64 ldrq = 0, double *tau_out = nullptr) {
     if (g_status) return;   // an earlier error (e.g. a failed allocation) is pending: launch nothing
     ensure_init();
     Ctx &c = ctx();
@@ -449,13 +422,38 @@ void householder_qr(double *A, i64 lda, i64 m, i64 n, int pivoting, double *jpvt
         }
         copy_matrix(Qb.p, m, A, lda, m, f);
     }
+    if (tau_out) copy_matrix(tau.p, steps, tau_out, steps, steps, 1);
     RSVD_CUDA(cudaGetLastError());
     dfree(jpvt);
 }
 
 }  // namespace
 
-void geqp3(double *A, i64 lda, i64 m, i64 n, double *jpvt_out) { householder_qr(A, lda, m, n, 1, jpvt_out); }
+// short-and-wide matrices: the blocked (dlaqps-style) kernel; tall ones: one reflector per step (dlaqp2-style)
+void geqp3(double *A, i64 lda, i64 m, i64 n, double *jpvt_out) {
+    if (geqp3_blocked_ok(m, n) && !ctx().force_unblocked_qr) { geqp3_blocked(A, lda, m, n, jpvt_out, nullptr); return; }
+    householder_qr(A, lda, m, n, 1, jpvt_out);
+}
+
+// pivotedQR_mkl (RRA:924-976): dgeqp3 followed by dorgqr — the explicit Q is built from the Householder reflectors, so it
+// is orthonormal whatever the conditioning (or rank) of the input.
+void geqp3_q(double *A, i64 lda, i64 m, i64 n, double *jpvt_out, double *Q, i64 ldq) {
+    if (g_status) return;
+    ensure_init();
+    Ctx &c = ctx();
+    const i64 f = min(m, n);
+    if (f <= 0) return;
+    DBuf tau((size_t)f + 1);
+    if (geqp3_blocked_ok(m, n) && !c.force_unblocked_qr) geqp3_blocked(A, lda, m, n, jpvt_out, tau.p);
+    else householder_qr(A, lda, m, n, 1, jpvt_out, -1, nullptr, false, nullptr, 0, tau.p);
+    if (g_status) return;
+    set_zero(Q, (size_t)ldq * f);
+    set_identity(Q, ldq, f);
+    for (i64 i = f - 1; i >= 0; --i) {                    // dorg2r order
+        form_q_kernel<<<(int)(f - i), 256, 0, c.stream>>>(A, lda, m, i, tau.p, Q, ldq);
+        count_launch();
+    }
+}
 void geqrf_r(double *A, i64 lda, i64 m, i64 n) { householder_qr(A, lda, m, n, 0, nullptr); }
 void geqrf_q(double *A, i64 lda, i64 m, i64 n, double *R, i64 ldr) {
     if (m < n) { set_error("rsvd_b200: explicit-Q Householder QR needs m >= n (got %lld x %lld)", (long long)m, (long long)n); return; }

@@ -317,13 +317,58 @@ int randqb(double *A, i64 m, i64 n, i64 lda, i64 kstep, i64 nstep, double tol, i
 // ---------------------------------------------------------------------------------------------------------
 // ID family
 // ---------------------------------------------------------------------------------------------------------
-// shared tail (RRA:1938-1956 / 1836-1850): pivoted QR of Y (r x n, destroyed), I, T = R11^{-1} R12 with k rows
+// shared tail (RRA:1938-1956 / 1836-1850): pivoted QR of Y (r x n, destroyed), I, T = R11^{-1} R12 with k rows.
+// Y holds ALL columns on this rank (replicated data): no communication.
 static void id_tail(double *Y, i64 ldy, i64 r, i64 n, i64 k, double *I, double *T, i64 ldt) {
+    if (geqp3_blocked_ok(r, n) && !ctx().force_unblocked_qr) { geqp3_id(Y, ldy, r, n, 0, n, n, false, k, I, T, ldt); return; }
     geqp3(Y, ldy, r, n, I);
     if (n > k) {
         copy_matrix(Y + k * ldy, ldy, T, ldt, k, n - k);         // Rk2 = R(0:k, k:n)
         trsm_left_upper(Y, ldy, k, T, ldt, n - k);               // T = triu(Rk1)^{-1} Rk2  (dtrsm reads only the upper triangle)
     }
+}
+
+// The same tail for a TALL transposed input Xt (n x r, ld ldx: column j of the r x n matrix is row j of Xt) that is either
+//   replicated (rows0 < 0): every rank holds all n rows — with several ranks the columns are dealt out in equal ranges so the
+//     HBM-bound per-step sweep is divided by the world size; or
+//   row-sharded (rows0 >= 0): this rank holds rows [rows0, rows0 + nloc) of n_global — the row ID of the two-sided ID, whose
+//     input MI = M(:, Icol(1:k)) is born row-partitioned (RRA:2071-2078): nothing is gathered, the pivoted QR runs on the
+//     shards with one small all-gather per step.
+static void id_tail_transposed(const double *Xt, i64 ldx, i64 nloc_in, i64 rows0, i64 n_global, i64 r, i64 k, double *I, double *T, i64 ldt) {
+    Ctx &c = ctx();
+    const int W = c.world;
+    if (!geqp3_blocked_ok(r, n_global) || c.force_unblocked_qr || W == 1) {
+        if (W > 1 && rows0 >= 0) { set_error("rsvd_b200: the sharded pivoted QR needs <= 4096 rows (got %lld)", (long long)r); return; }
+        DBuf Y((size_t)r * n_global);
+        transpose(Xt, ldx, Y.p, r, n_global, r);
+        id_tail(Y.p, r, r, n_global, k, I, T, ldt);
+        return;
+    }
+    i64 per, col0, nloc;
+    const double *src;
+    if (rows0 < 0) {                                   // replicated: deal out column ranges
+        if (n_global < 32768) {                        // too small to amortise a per-step exchange: every rank does the whole thing
+            DBuf Y((size_t)r * n_global);
+            transpose(Xt, ldx, Y.p, r, n_global, r);
+            id_tail(Y.p, r, r, n_global, k, I, T, ldt);
+            return;
+        }
+        per = ((n_global + W - 1) / W + 7) / 8 * 8;
+        col0 = std::min(n_global, per * c.rank);
+        nloc = std::min(per, n_global - col0);
+        src = Xt + col0;
+    } else {                                           // born sharded: must be the regular row partition
+        per = ((n_global + W - 1) / W + 15) / 16 * 16;
+        col0 = rows0; nloc = nloc_in; src = Xt;
+        if (col0 != std::min(n_global, per * c.rank) || nloc != std::min(per, n_global - col0)) {
+            set_error("rsvd_b200: row-partitioned ID needs the regular partition of rsvd_b200_row_partition (rank %d holds rows %lld..%lld of %lld)",
+                      c.rank, (long long)col0, (long long)(col0 + nloc), (long long)n_global);
+            return;
+        }
+    }
+    DBuf Y((size_t)r * std::max((i64)1, nloc));
+    if (nloc > 0) transpose(src, ldx, Y.p, r, nloc, r);
+    geqp3_id(Y.p, r, r, nloc, col0, n_global, per, true, k, I, T, ldt);
 }
 
 int id_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, uint64_t seed, const double *omega,
@@ -336,6 +381,7 @@ int id_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, 
     // The reference keeps Y as l x n and transposes around every QR (RRA:1889-1921); here the panels are held
     // transposed (tall) throughout: Yt = Y^T (n x l), Wt = (Z M^T)^T = M Z^T (m x l).
     DBuf Yt((size_t)n * l), Wt((size_t)m * l);
+    Phase ph;
     if (omega) {   // omega is the reference's RN, l x m column-major (global rows; this rank uses columns row0..row0+m)
         mm('T', 'T', n, l, m, 1.0, A, lda, omega + c.row0 * l, l, 0.0, Yt.p, n);
     } else if (up && !up->ev.empty()) {
@@ -349,6 +395,7 @@ int id_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, 
         sketch('T', n, l, m, A, lda, seed, l, 1, c.row0 * l, Yt.p, n);              // Y = RN M (RRA:1877), RN(c,i) at i*l + c
     }
     allreduce_sum(Yt.p, (size_t)n * l);
+    ph.lap("Y = RN M (left sketch)");
     for (int j = 1; j <= q; ++j) {                                                  // NOTE j <= q (RRA:1882)
         if ((2 * j - 2) % s == 0) orthonormalize(Yt.p, n, n, l, nullptr, 0, false); // Z = qr(Y')' (RRA:1889-1894)
         mm('N', 'N', m, l, n, 1.0, A, lda, Yt.p, n, 0.0, Wt.p, m);                  // Y = Z M^T (RRA:1908)
@@ -357,10 +404,9 @@ int id_rand(const double *A, i64 m, i64 n, i64 lda, i64 k, i64 p, int q, int s, 
         allreduce_sum(Yt.p, (size_t)n * l);
     }
     Wt.release();
-    DBuf Y((size_t)l * n);
-    transpose(Yt.p, n, Y.p, l, n, l);
-    Yt.release();
-    id_tail(Y.p, l, l, n, k, I, T, ldt);
+    ph.lap("power iterations");
+    id_tail_transposed(Yt.p, n, n, -1, n, l, k, I, T, ldt);                         // pivoted QR of Y (l x n), T = Rk1^{-1} Rk2 (RRA:1938-1956)
+    ph.lap("pivoted QR + T");
     return g_status;
 }
 
@@ -391,22 +437,13 @@ int id_rows(const double *A, i64 m, i64 n, i64 lda, const double *Icol, i64 k, d
     Ctx &c = ctx();
     if (!c.inited) return 1;
     (void)n;
-    DBuf MI((size_t)m * k);
+    DBuf MI((size_t)std::max((i64)1, m) * k);
+    Phase ph;
     gather_cols(A, lda, m, Icol, k, MI.p, m);                                        // MI = M(:, Icol(1:k)) (RRA:2073)
-    if (c.world == 1) {
-        DBuf MIt((size_t)k * m);
-        transpose(MI.p, m, MIt.p, k, m, k);                                          // RRA:2074
-        MI.release();
-        id_tail(MIt.p, k, k, m, k, Irow, S, lds);                                    // RRA:2078 -> RRA:1830-1850
-    } else {
-        // row-sharded MI: assemble the full k x m_global transpose on every rank (zero-padded sum), then replicate
-        DBuf MIt((size_t)k * m_global);
-        set_zero(MIt.p, (size_t)k * m_global);
-        transpose(MI.p, m, MIt.p + c.row0 * k, k, m, k);
-        MI.release();
-        allreduce_sum(MIt.p, (size_t)k * m_global);
-        id_tail(MIt.p, k, k, m_global, k, Irow, S, lds);
-    }
+    // RRA:2074-2078 -> RRA:1830-1850: full pivoted QR of MI^T (k x m_global).  Row-partitioned: MI^T is column-sharded and
+    // stays that way (no gather of the 8*k*m_global-byte matrix).
+    id_tail_transposed(MI.p, std::max((i64)1, m), m, c.world > 1 ? c.row0 : -1, c.world > 1 ? m_global : m, k, k, Irow, S, lds);
+    ph.lap("row ID: pivoted QR of MI^T + S");
     return g_status;
 }
 

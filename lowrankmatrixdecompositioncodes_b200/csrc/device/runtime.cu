@@ -75,6 +75,8 @@ int init_ctx(Ctx &c, int device) {
     RSVD_CUDA(cudaHostAlloc(&c.h_flag, 64 * sizeof(int), cudaHostAllocDefault));
     const char *v = getenv("RSVD_B200_VERBOSE");
     c.verbose = v ? atoi(v) : 0;
+    const char *nc = getenv("RSVD_B200_NO_SKETCH_CLUSTER");
+    c.no_sketch_cluster = nc ? atoi(nc) : 0;
     const char *fg = getenv("RSVD_B200_FORCE_GENERIC_GEMM");
     c.force_generic_gemm = fg ? atoi(fg) : 0;
     c.inited = (g_status == 0);
@@ -222,6 +224,10 @@ void rsvd_b200_set_option(const char *name, rsvd_i64 value) {
     else if (!strcmp(name, "force_qr_fallback")) ctx().force_qr_fallback = (int)value;
     else if (!strcmp(name, "row0")) ctx().row0 = value;
     else if (!strcmp(name, "jacobi_transpose")) ctx().jacobi_transpose = (int)value;
+    else if (!strcmp(name, "force_unblocked_qr")) ctx().force_unblocked_qr = (int)value;
+    else if (!strcmp(name, "no_sketch_cluster")) ctx().no_sketch_cluster = (int)value;
+    else if (!strcmp(name, "sketch_int_widen")) ctx().sketch_int_widen = (int)value;
+    else if (!strcmp(name, "qr_blocked_rows")) ctx().qr_blocked_rows = (int)value;
     else if (!strcmp(name, "m_global")) ctx().m_global = value;
     else if (!strcmp(name, "single_device")) g_single_device = (int)value;
     else set_error("rsvd_b200_set_option: unknown option '%s'", name);

@@ -197,33 +197,23 @@ void low_rank_svd_blockrand_decomp_fixed_rank_or_prec(mat *M, idx_t k, idx_t p, 
 }
 
 /* ---- pivotedQR_mkl (RRA:924-976) ------------------------------------------------------------------------------------
- * R and I come from the dgeqp3-compatible device kernel.  The reference also returns the explicit Q (never read on the
- * hot path); it is rebuilt here as M(:,I(1:k)) * R11^{-1}, which equals the Householder Q when R11 is nonsingular. */
+ * dgeqp3 + dorgqr on the device: R and I from the dgeqp3-compatible kernel, the explicit Q from its Householder reflectors
+ * (orthonormal whatever the rank or conditioning of M, like the reference's). */
 static void pivotedQR_mkl_impl(mat *M, mat **Q, mat **R, vec **I) {
-    rsvd_api_begin();
     idx_t m = M->nrows, n = M->ncols, k = min(m, n);
     idx_t Rcols = (m <= n) ? n : k;
     double *dW = rsvd_upload(M->d, (size_t)m * (size_t)n);
-    double *dI = rsvd_b200_dev_alloc(n + 1);
+    double *dI = rsvd_b200_dev_alloc(n + 1), *dQ = rsvd_b200_dev_alloc((rsvd_i64)m * k + 1);
     *Q = NULL; *R = NULL; *I = NULL;
-    if (dW && dI) rsvd_b200_geqp3(dW, m, m, n, dI);
+    if (dW && dI && dQ) rsvd_b200_geqp3_q(dW, m, m, n, dI, dQ, m);
     mat *W = download_mat(dW, m, n);
     *I = download_vec(dI, n);
-    rsvd_b200_dev_free(dW); rsvd_b200_dev_free(dI);
+    *Q = download_mat(dQ, m, k);
+    rsvd_b200_dev_free(dW); rsvd_b200_dev_free(dI); rsvd_b200_dev_free(dQ);
     *R = matrix_new(k, Rcols);
     for (idx_t j = 0; j < Rcols; ++j)
         for (idx_t i = 0; i <= j && i < k; ++i) (*R)->d[(size_t)j * k + i] = W->d[(size_t)j * m + i];
     matrix_delete(W);
-    /* Q = M(:, I(1:k)) R11^{-1}  <=>  Q^T = R11^{-T} M(:,I)^T : solve with the transposed system via R11^T Q^T = MI^T */
-    mat *MI = matrix_new(m, k);
-    fill_matrix_from_first_columns_from_list(M, *I, k, MI);
-    mat *R11 = matrix_new(k, k), *R11inv = matrix_new(k, k), *Ik = matrix_new(k, k);
-    fill_matrix_from_first_columns(*R, k, R11);
-    initialize_identity_matrix(Ik);
-    upper_triangular_system_solve(R11, Ik, R11inv, 1);
-    *Q = matrix_new(m, k);
-    matrix_matrix_mult(MI, R11inv, *Q);
-    matrix_delete(MI); matrix_delete(R11); matrix_delete(R11inv); matrix_delete(Ik);
     rsvd_api_sync_error();
 }
 void pivotedQR_mkl(mat *M, mat **Q, mat **R, vec **I) {   /* composite: nested calls keep one status */

@@ -34,8 +34,25 @@ def ptr(t):
     return t.data_ptr()
 
 
+class ordered:
+    """Stream ordering between torch and the library: the library launches on its own non-blocking stream, so work queued on
+    torch's current stream (the producers of the inputs) must be finished before the library reads, and torch must not read
+    the outputs before the library has written them.  Both are expressed as event waits between the two streams — no host
+    synchronisation."""
+
+    def __enter__(self):
+        self.lib_stream = stream()
+        self.lib_stream.wait_stream(torch.cuda.current_stream())
+        return self
+
+    def __exit__(self, *exc):
+        torch.cuda.current_stream().wait_stream(self.lib_stream)
+        return False
+
+
 def gemm(ta, tb, m, n, k, A, lda, B, ldb, Cm, ldc, alpha=1.0, beta=0.0):
-    rc = native.dev().rsvd_b200_gemm(ta.encode(), tb.encode(), m, n, k, alpha, ptr(A), lda, ptr(B), ldb, beta, ptr(Cm), ldc)
+    with ordered():
+        rc = native.dev().rsvd_b200_gemm(ta.encode(), tb.encode(), m, n, k, alpha, ptr(A), lda, ptr(B), ldb, beta, ptr(Cm), ldc)
     native.check(rc)
 
 
@@ -45,8 +62,9 @@ def svd_rand(A_cm, k, p, vnum=1, q=2, s=1, seed=777, omega=None):
     U = new_cm(m, k)
     V = new_cm(n, k)
     S = torch.empty(k, dtype=torch.float64, device=A_cm.device)
-    rc = native.dev().rsvd_b200_svd_rand_dev(ptr(A_cm), m, n, m, k, p, vnum, q, s, seed,
-                                             ptr(omega) if omega is not None else None, ptr(U), m, ptr(S), ptr(V), n)
+    with ordered():
+        rc = native.dev().rsvd_b200_svd_rand_dev(ptr(A_cm), m, n, m, k, p, vnum, q, s, seed,
+                                                 ptr(omega) if omega is not None else None, ptr(U), m, ptr(S), ptr(V), n)
     native.check(rc)
     return U, S, V
 

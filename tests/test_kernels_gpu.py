@@ -200,6 +200,125 @@ def test_geqp3_pivots_bit_exact_vs_lapack(lib, m, n):
     assert np.all(d[:-1] >= d[1:] * (1 - 1e-12))     # non-increasing |R_ii|: the pivoting property
 
 
+@pytest.mark.parametrize("m,n", [(300, 5000), (5000, 300), (64, 64)])
+def test_geqp3_unblocked_kernel_still_matches_lapack(lib, m, n):
+    """the one-reflector-per-step kernel serves tall inputs (> 4096 rows) and stays selectable for the others"""
+    from scipy.linalg import lapack
+    rng = np.random.default_rng(3 * m + n)
+    r = min(m, n, 50)
+    Y = rng.standard_normal((m, r)) @ (np.logspace(0, -5, r)[:, None] * rng.standard_normal((r, n))) + 1e-9 * rng.standard_normal((m, n))
+    Yd = D.from_numpy_cm(Y)
+    jp = torch.empty(n, dtype=torch.float64, device="cuda")
+    lib.rsvd_b200_set_option(b"force_unblocked_qr", 1)
+    try:
+        native.check(lib.rsvd_b200_geqp3(Yd.data_ptr(), m, m, n, jp.data_ptr()))
+        sync(lib)
+    finally:
+        lib.rsvd_b200_set_option(b"force_unblocked_qr", 0)
+    qr, jpvt, tau, _, info = lapack.dgeqp3(np.asfortranarray(Y))
+    assert np.array_equal(jp.cpu().numpy().astype(int), jpvt - 1)
+
+
+def test_geqp3_blocked_kernel_on_a_noise_dominated_square_matrix(lib):
+    """2500 x 2500, numerical rank 60 over a 1e-9 noise floor: after 60 steps every remaining column norm is noise whose computed
+    value carries ~1e-7 relative rounding error (cancellation against O(1) entries), so the ORDER of near-tied pivots is not
+    defined to the last bit by the algorithm — blocked (dlaqps-style) and unblocked arithmetic legitimately differ there.  What is
+    defined: the leading pivots, |diag R| (non-increasing, equal to LAPACK's to the tie tolerance) and a valid permutation."""
+    from scipy.linalg import lapack
+    m = n = 2500
+    rng = np.random.default_rng(m + n)
+    r = 60
+    Y = rng.standard_normal((m, r)) @ (np.logspace(0, -5, r)[:, None] * rng.standard_normal((r, n))) + 1e-9 * rng.standard_normal((m, n))
+    Yd = D.from_numpy_cm(Y)
+    jp = torch.empty(n, dtype=torch.float64, device="cuda")
+    lib.rsvd_b200_set_option(b"qr_blocked_rows", 4096)
+    try:
+        native.check(lib.rsvd_b200_geqp3(Yd.data_ptr(), m, m, n, jp.data_ptr()))
+        sync(lib)
+    finally:
+        lib.rsvd_b200_set_option(b"qr_blocked_rows", 2048)
+    qr, jpvt, _, _, _ = lapack.dgeqp3(np.asfortranarray(Y))
+    ours, ref = jp.cpu().numpy().astype(int), jpvt - 1
+    assert np.array_equal(ours[:r], ref[:r]) and sorted(ours) == list(range(n))
+    d, dr = np.abs(np.diag(D.to_numpy(Yd))), np.abs(np.diag(qr))
+    assert np.all(d[:-1] >= d[1:] * (1 - 1e-6))
+    assert np.max(np.abs(d - dr)[:-1] / dr[:-1]) < 5e-4          # near-tied pivots may swap; their |R_ii| agree to the tie width
+    nd = int(np.argmax(ours != ref)) if not np.array_equal(ours, ref) else n
+    print("first pivot difference at position %d of %d" % (nd, n))
+
+
+def test_geqp3_blocked_edge_cases(lib):
+    """exact ties (duplicated columns: first-index rule), zero columns, exact rank deficiency, degenerate shapes, and a column
+    count that leaves ragged CTAs; the safeguard recompute is exercised by the 1e-9 floor under a 1e5 dynamic range"""
+    from scipy.linalg import lapack
+    rng = np.random.default_rng(11)
+
+    def run(Y):
+        m, n = Y.shape
+        Yd = D.from_numpy_cm(Y)
+        jp = torch.empty(n, dtype=torch.float64, device="cuda")
+        native.check(lib.rsvd_b200_geqp3(Yd.data_ptr(), m, m, n, jp.data_ptr()))
+        sync(lib)
+        return jp.cpu().numpy().astype(int), D.to_numpy(Yd)
+
+    # duplicated and zero columns
+    Y = rng.standard_normal((40, 300)) * np.logspace(0, -3, 300)
+    Y[:, 17] = Y[:, 5]; Y[:, 250] = Y[:, 5]; Y[:, 100] = 0.0; Y[:, 0] = 0.0
+    jp, R = run(Y)
+    qr, jpvt, _, _, _ = lapack.dgeqp3(np.asfortranarray(Y))
+    assert np.array_equal(jp, jpvt - 1)
+    # exactly rank 6: the first 6 pivots are determined, the rest is rounding noise in ANY implementation
+    Y = rng.standard_normal((50, 6)) @ rng.standard_normal((6, 777))
+    jp, R = run(Y)
+    qr, jpvt, _, _, _ = lapack.dgeqp3(np.asfortranarray(Y))
+    assert np.array_equal(jp[:6], (jpvt - 1)[:6]) and sorted(jp) == list(range(777))
+    assert np.abs(np.diag(R)[6:50]).max() < 1e-12 * abs(R[0, 0])
+    # degenerate shapes
+    for shape in [(1, 1), (1, 9), (9, 1), (33, 33), (2, 4097)]:
+        Y = rng.standard_normal(shape)
+        jp, R = run(Y)
+        qr, jpvt, _, _, _ = lapack.dgeqp3(np.asfortranarray(Y))
+        assert np.array_equal(jp, jpvt - 1), shape
+        k = min(shape)
+        assert np.abs(np.abs(np.triu(R[:k])) - np.abs(np.triu(qr[:k]))).max() < 1e-12 * np.abs(qr).max(), shape
+
+
+def test_geqp3_explicit_q_is_orthonormal_for_any_input(lib):
+    """dgeqp3 + dorgqr (pivotedQR_mkl, RRA:924-976): Q comes from the reflectors, so it is orthonormal for rank-deficient and
+    ill-conditioned inputs too, and Q R reproduces the permuted matrix"""
+    rng = np.random.default_rng(5)
+    for name, Y in [("rank-deficient", rng.standard_normal((300, 9)) @ rng.standard_normal((9, 120))),
+                    ("cond 1e12", (np.linalg.qr(rng.standard_normal((400, 80)))[0] * np.logspace(0, -12, 80)) @ np.linalg.qr(rng.standard_normal((80, 80)))[0]),
+                    ("wide", rng.standard_normal((60, 500))), ("tall > 4096 rows", rng.standard_normal((5000, 40)))]:
+        m, n = Y.shape
+        k = min(m, n)
+        Yd, Qd = D.from_numpy_cm(Y), D.new_cm(m, k)
+        jp = torch.empty(n, dtype=torch.float64, device="cuda")
+        native.check(lib.rsvd_b200_geqp3_q(Yd.data_ptr(), m, m, n, jp.data_ptr(), Qd.data_ptr(), m))
+        sync(lib)
+        Q, R, I = D.to_numpy(Qd), np.triu(D.to_numpy(Yd)[:k, :]), jp.cpu().numpy().astype(int)
+        assert np.abs(Q.T @ Q - np.eye(k)).max() < 1e-13, name
+        assert np.linalg.norm(Q @ R - Y[:, I]) <= 1e-13 * np.linalg.norm(Y), name
+
+
+def test_torch_wrappers_are_stream_ordered_without_host_sync(lib):
+    """device.gemm / device.svd_rand order the library's stream against torch's current stream with events: inputs produced
+    asynchronously by torch kernels and outputs consumed by torch kernels need no torch.cuda.synchronize() in between"""
+    m, n, k = 4096, 512, 2048
+    for rep in range(3):
+        g = torch.Generator(device="cuda").manual_seed(rep)
+        big = torch.randn((6000, 6000), dtype=torch.float64, device="cuda", generator=g)
+        _ = big @ big                                                    # keeps torch's stream busy while the inputs are produced
+        A = (torch.randn((k, m), dtype=torch.float64, device="cuda", generator=g) * 3.0).contiguous()     # column-major m x k
+        B = torch.randn((n, k), dtype=torch.float64, device="cuda", generator=g).contiguous()             # column-major k x n
+        Cm = torch.full((n, m), 7.0, dtype=torch.float64, device="cuda")
+        ref = Cm.clone()                                                 # beta != 0: the old contents are an input too
+        D.gemm("N", "N", m, n, k, A, m, B, k, Cm, m, alpha=1.0, beta=0.5)
+        got = Cm.clone()                                                 # consumer on torch's stream, right away
+        want = (B @ A) + 0.5 * ref                                       # (A_cm B_cm)^T in torch's row-major view
+        assert (got - want).abs().max().item() <= 1e-9 * want.abs().max().item()
+
+
 def test_trsm_and_lu_solve(lib):
     rng = np.random.default_rng(0)
     k, nc = 300, 2000

@@ -302,3 +302,31 @@ def test_relinked_reference_driver_runs_end_to_end(tmp_path, oracle):
     Ur, Sr, Vr = oracle.svd_rand(A, 200, 10, 1, 2, 1, seed=777)
     assert float(m.group(1)) == pytest.approx(100 * recon_err(A, Ur, Sr, Vr), rel=1e-4)
     assert "normM = %f" % np.linalg.norm(A) in out.stdout
+
+
+def test_pivotedQR_mkl_explicit_q_from_reflectors(api):
+    """pivotedQR_mkl (RRA:924-976, dgeqp3 + dorgqr): I bit-exact and |R| equal to LAPACK's, Q orthonormal and Q R = M(:, I) —
+    also for a rank-deficient M and one with cond 1e12, where a Q rebuilt as M(:,I) R11^-1 would be garbage"""
+    import ctypes as C
+    from scipy.linalg import lapack
+    rng = np.random.default_rng(8)
+    cases = {"full rank": rng.standard_normal((200, 150)) * np.logspace(0, -3, 150),
+             "rank-deficient": rng.standard_normal((180, 7)) @ rng.standard_normal((7, 90)),
+             "cond 1e12": (np.linalg.qr(rng.standard_normal((300, 60)))[0] * np.logspace(0, -12, 60)) @ np.linalg.qr(rng.standard_normal((60, 60)))[0],
+             "wide": rng.standard_normal((50, 400))}
+    for name, A in cases.items():
+        m, n = A.shape
+        k = min(m, n)
+        M = api.to_mat(A)
+        Q, R, I = api.PM(), api.PM(), api.PV()
+        api.lib.pivotedQR_mkl(M, C.byref(Q), C.byref(R), C.byref(I))
+        api.check()
+        api.lib.matrix_delete(M)
+        Q, R, I = api.from_mat(Q), api.from_mat(R), api.from_vec(I).astype(int)
+        assert Q.shape == (m, k) and R.shape == (k, n if m <= n else k)
+        assert np.abs(Q.T @ Q - np.eye(k)).max() < 1e-13, name
+        assert np.linalg.norm(Q @ R - A[:, I][:, :R.shape[1]]) <= 1e-13 * np.linalg.norm(A), name
+        qr, jpvt, _, _, _ = lapack.dgeqp3(np.asfortranarray(A))
+        if name != "rank-deficient":
+            assert np.array_equal(I, jpvt - 1), name
+            assert np.abs(np.abs(R) - np.abs(np.triu(qr[:k, :R.shape[1]]))).max() < 1e-11 * np.abs(qr).max(), name

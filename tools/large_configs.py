@@ -55,29 +55,40 @@ def sync():
 
 
 if what == "c3":
+    # BASELINE configs[2]: blockrand QB, autorank TOL = 1e-6 (ABSOLUTE Frobenius norm, RRA:1773-1775), kstep = 200, on a matrix
+    # whose residual really drops below the tolerance: exact rank 600 + a 1e-12 noise floor (||noise||_F = 1e-12 sqrt(mn) = 1e-7)
     m = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
     n, kstep, q, s = 50000, 200, 2, 1
-    A, sig = gen(m, n)
+    A, sig = gen(m, n, r=600, lo=-2.0, noise=1e-12)
     normA = lib.rsvd_b200_frob_norm(A.data_ptr(), m, m, n)
-    tol = float(torch.sqrt((sig[600:] ** 2).sum()).item()) * 1.5     # reached after ~3 blocks of 200
+    tol = 1e-6
     cap = 2000
     Q = torch.zeros((cap, m), dtype=torch.float64, device="cuda")
     B = torch.zeros((n, cap), dtype=torch.float64, device="cuda")
     fr = C.c_longlong(0)
-    print("C3: randQB_pb_new tolerance mode on %d x %d (%.1f GB), kstep=%d q=%d, ||A||_F=%.4f, TOL=%.4g (absolute)" % (m, n, 8e-9 * m * n, kstep, q, normA, tol), flush=True)
+    print("C3: randQB_pb_new tolerance mode on %d x %d (%.1f GB), kstep=%d q=%d, ||A||_F=%.4f, TOL=%.1e (absolute)" % (m, n, 8e-9 * m * n, kstep, q, normA, tol), flush=True)
     lib.rsvd_b200_set_option(b"verbose", 1)
     sync()
     t0 = time.time()
     native.check(lib.rsvd_b200_randqb_dev(A.data_ptr(), m, n, m, kstep, 0, tol, q, s, 777, Q.data_ptr(), m, B.data_ptr(), cap, C.byref(fr)))
     sync()
     dt = time.time() - t0
+    lib.rsvd_b200_set_option(b"verbose", 0)
     f = int(fr.value)
     res = lib.rsvd_b200_frob_norm(A.data_ptr(), m, m, n)     # A now holds the residual A - QB
-    passes = (f // kstep) * (2 * q + 3)
-    print("   frank=%d  time %.3f s  ||A-QB||_F=%.4g (< TOL: %s)  %.1f TFLOP/s over %d width-%d passes" %
-          (f, dt, res, res < tol, passes * 2.0 * m * n * kstep / dt / 1e12, passes, kstep), flush=True)
+    nblk = f // kstep
+    passes = nblk * (2 * q + 3)
+    peak = max(lib.rsvd_b200_fp64_peak_tflops(4000, 0), lib.rsvd_b200_fp64_peak_tflops(4000, 1))
+    bound = (2 * q + 3) * 2.0 * m * n * kstep / (peak * 1e12)
+    print("   frank=%d  time %.3f s = %.3f s per block step  ||A-QB||_F=%.4g (< TOL: %s)  %.1f TFLOP/s over %d width-%d passes" %
+          (f, dt, dt / nblk, res, res < tol, passes * 2.0 * m * n * kstep / dt / 1e12, passes, kstep), flush=True)
+    print("   per-step bound 7 passes x 2mn*kstep / measured FP64 peak (%.1f TFLOP/s) = %.3f s; measured / bound = %.3f" % (peak, bound, dt / nblk / bound), flush=True)
     Qf = Q[:f]
     print("   ||Q^T Q - I||_max = %.2e" % (Qf @ Qf.t() - torch.eye(f, dtype=torch.float64, device="cuda")).abs().max().item())
+    # SVD tail from the residual (no second copy of M): sigma against the construction
+    k = 400
+    U = D.new_cm(m, k); V = D.new_cm(n, k); Sv = torch.empty(k, dtype=torch.float64, device="cuda")
+    # (the tail is reached through the host-level API in production; here the device-resident pieces are timed)
 
 elif what == "c4":
     mg = int(sys.argv[2]) if len(sys.argv) > 2 else 200000      # GLOBAL rows
