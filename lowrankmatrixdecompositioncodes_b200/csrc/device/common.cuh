@@ -47,7 +47,6 @@ struct Ctx {
     int verbose = 0;
     int force_generic_gemm = 0;
     int force_qr_fallback = 0;
-    int sketch_int_widen = 0;        // experiment: widen the generated float32 normals to double with integer ops (no F2F on the FP64 pipe)
     int no_sketch_cluster = 0;       // option: sketch kernel without 2-CTA clusters (each CTA generates its own Omega stages)
     int qr_blocked_rows = 2048;      // inputs with at most this many rows go to the blocked pivoted QR (geqp3_blocked.cu)
     int force_unblocked_qr = 0;      // option: pivoted QR through the one-reflector-per-step kernel even for short-wide inputs

@@ -144,7 +144,7 @@ bool gemm_tma_try(const Gemm &g) {
     p.cl = 0;
     if (g.philox && tm >= 2 && !ctx().no_sketch_cluster) {
         const int cs = sketch_cluster_slots(nb_tile, ta);
-        if (cs >= 8) { p.cl = ctx().sketch_int_widen ? 2 : 1; slots = cs; tiles = ((tm + 1) / 2) * T; }
+        if (cs >= 8) { p.cl = 1; slots = cs; tiles = ((tm + 1) / 2) * T; }
     }
     p.b_upper = (g.b_upper && !g.philox) ? 1 : 0;
     p.sym = 0;

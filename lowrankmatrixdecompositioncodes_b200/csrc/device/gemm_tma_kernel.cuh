@@ -125,17 +125,6 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// float -> double widening without the FP64 pipe (F2F.F64.F32 shares it with the consumers' DMMAs): exact for zeros and normal
-// floats — the only values Box-Muller on (0,1] uniforms produces besides (never reached) subnormals, which flush to signed zero
-__device__ __forceinline__ double widen_int(float f) {
-    const uint32_t u = __float_as_uint(f);
-    const uint32_t mag = u & 0x7fffffffu;
-    uint32_t hi = (mag >> 3) + 0x38000000u;                 // exponent rebias 127 -> 1023, top 20 mantissa bits
-    if (mag < 0x00800000u) hi = 0u;                          // zero (and subnormal) -> zero
-    return __hiloint2double((int)(hi | (u & 0x80000000u)), (int)(mag < 0x00800000u ? 0u : (u << 29)));
-}
-template <bool INTW> __device__ __forceinline__ double widen(float f) { return INTW ? widen_int(f) : (double)f; }
-
 // byte offset of element (column j, k index kk) inside a K-major [col][16 k] stage under SWIZZLE_128B
 __device__ __forceinline__ uint32_t bswz(int j, int kk) {
     return (uint32_t)(j * 128 + ((((kk >> 1) ^ (j & 7))) << 4) + (kk & 1) * 8);
@@ -155,7 +144,7 @@ __device__ __forceinline__ void decode_unit(const TmaP &p, int unit, int &tile, 
 // Philox + Box-Muller work per CTA halves.  full = expect_tx arrive + one elected lane per generator warp; empty counts the
 // consumer warps of both CTAs.
 template <bool A_KMAJOR, bool PHILOX, int NB, bool CL = false>
-__global__ void __launch_bounds__(PHILOX ? NTHREADS_PHILOX : NTHREADS, 1)
+__global__ void __launch_bounds__((PHILOX && !CL) ? NTHREADS_PHILOX : NTHREADS, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TmaP p) {
     static_assert(!CL || PHILOX, "clusters are only used by the sketch kernel");
     extern __shared__ unsigned char smem_raw[];
@@ -194,13 +183,14 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (CL) cluster_sync_all();            // the peer's barriers exist before anything is signalled remotely
     const uint32_t peer = crank ^ 1u;
 
-    constexpr int NPWG = PHILOX ? 2 : 1;     // producer warpgroups
+    constexpr int NPWG = (PHILOX && !CL) ? 2 : 1;     // producer warpgroups (a cluster CTA generates half a stage: one suffices, and the
+                                                      // consumers keep the 208 registers of the plain kernel)
     if (warp < 4 * NPWG) {
         // ===================== producer warpgroup(s) =====================
         // sketch mode: generating one Omega tile costs ~1.3x the DMMA time of a stage for a single warpgroup (latency-
         // bound Philox + Box-Muller chains), so two warpgroups take alternate stages.
         if (PHILOX) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-        else asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");     // (launch allocation: 168 with 384 threads, 128 with 512)
         const int pw = warp >> 2;                // which producer warpgroup
         const int ptid = tid & 127;              // thread index inside it
         if (PHILOX || tid == 0) {
@@ -242,9 +232,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                     for (int qd = 0; qd < 2; ++qd) {
                                         const int ch = 4 * (int)crank + 2 * qd;       // 16-byte chunk index of k = k0h + 4 qd
                                         const uint32_t o0 = (uint32_t)(j * 128 + ((ch ^ (j & 7)) << 4)), o1 = (uint32_t)(j * 128 + (((ch + 1) ^ (j & 7)) << 4));
-                                        double a0, a1, a2, a3;
-                                        if (p.cl == 2) { a0 = widen_int(z[qd][0]); a1 = widen_int(z[qd][1]); a2 = widen_int(z[qd][2]); a3 = widen_int(z[qd][3]); }
-                                        else { a0 = (double)z[qd][0]; a1 = (double)z[qd][1]; a2 = (double)z[qd][2]; a3 = (double)z[qd][3]; }
+                                        const double a0 = (double)z[qd][0], a1 = (double)z[qd][1], a2 = (double)z[qd][2], a3 = (double)z[qd][3];
                                         sts128(bbase + o0, a0, a1); sts128(bbase + o1, a2, a3);
                                         stas128(rbase + o0, a0, a1, rbar); stas128(rbase + o1, a2, a3, rbar);
                                     }
@@ -341,7 +329,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
     } else {
         // ===================== consumer warpgroups =====================
-        if (PHILOX) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+        if (PHILOX && !CL) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+        else if (PHILOX) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");     // 128 x 88 + 256 x 200 <= 64K registers
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         const int cw = warp - 4 * NPWG;           // rows [16*cw, 16*cw+16) of the tile, all columns
         const int g = lane >> 2, t = lane & 3;
@@ -522,7 +511,7 @@ bool launch_tma(bool a_kmajor, bool philox, const CUtensorMap &ma, const CUtenso
         if (e != cudaSuccess) { (void)cudaGetLastError(); return false; }
         if (p.cl) {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(philox ? NTHREADS_PHILOX : NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = ctx().stream;
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = ctx().stream;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
@@ -546,7 +535,7 @@ int max_sketch_clusters(bool a_kmajor) {
     auto q = [&](auto kern) -> int {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * 148); cfg.blockDim = dim3(NTHREADS_PHILOX); cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.gridDim = dim3(2 * 148); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;

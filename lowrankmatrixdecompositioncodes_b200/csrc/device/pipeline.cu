@@ -483,8 +483,31 @@ int cur_from_id(const double *A, i64 m, i64 n, i64 lda, const double *Icol, cons
     transpose(R, ldr, Rt.p, n, k, n);
     mm('T', 'N', k, k, n, 1.0, Rt.p, n, Rt.p, n, 0.0, RRt.p, k);                     // R R^T (RRA:2247)
     mm('T', 'N', k, k, n, 1.0, Rt.p, n, V.p, n, 0.0, RV.p, k);                       // R V   (RRA:2248)
-    int info = lu_solve(RRt.p, k, k, RV.p, k, k);                                    // (R R^T) U^T = R V (RRA:2250)
-    if (info) set_error("rsvd_b200: CUR core solve hit a zero pivot at column %d", info);
+    // (R R^T) U^T = R V (RRA:2250, dgesv in the reference).  R R^T is symmetric positive definite whenever the k selected rows are
+    // independent, so the solve goes through the blocked Cholesky factor G^T G and its inverse (three k^3 GEMM-speed steps)
+    // instead of the one-CTA LU, which at k = 1000 took 0.3 s — as long as the whole two-sided ID; the LU with partial pivoting
+    // remains the fallback when the Cholesky factorisation breaks down (numerically dependent rows).
+    bool solved = false;
+    {
+        DBuf G((size_t)k * k), Ginv((size_t)k * k), Y((size_t)k * k), X((size_t)k * k), Res((size_t)k * k);
+        copy_matrix(RRt.p, k, G.p, k, k, k);
+        if (potrf_upper(G.p, k, k) == 0 && !g_status) {
+            trtri_upper(G.p, k, k, Ginv.p, k);
+            mm('T', 'N', k, k, k, 1.0, Ginv.p, k, RV.p, k, 0.0, Y.p, k);           // Y = G^{-T} (R V)
+            mm('N', 'N', k, k, k, 1.0, Ginv.p, k, Y.p, k, 0.0, X.p, k);            // X = G^{-1} Y
+            // one step of iterative refinement against the unfactored R R^T: the accuracy of a backward-stable solver
+            copy_matrix(RV.p, k, Res.p, k, k, k);
+            mm('N', 'N', k, k, k, -1.0, RRt.p, k, X.p, k, 1.0, Res.p, k);          // Res = R V - (R R^T) X
+            mm('T', 'N', k, k, k, 1.0, Ginv.p, k, Res.p, k, 0.0, Y.p, k);
+            mm('N', 'N', k, k, k, 1.0, Ginv.p, k, Y.p, k, 1.0, X.p, k);            // X += G^{-1} G^{-T} Res
+            copy_matrix(X.p, k, RV.p, k, k, k);                                    // U^T
+            solved = true;
+        }
+    }
+    if (!solved) {
+        int info = lu_solve(RRt.p, k, k, RV.p, k, k);
+        if (info) set_error("rsvd_b200: CUR core solve hit a zero pivot at column %d", info);
+    }
     transpose(RV.p, k, U, ldu, k, k);                                                // U = (U^T)^T (RRA:2252)
     return g_status;
 }

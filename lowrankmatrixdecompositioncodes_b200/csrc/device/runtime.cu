@@ -226,7 +226,6 @@ void rsvd_b200_set_option(const char *name, rsvd_i64 value) {
     else if (!strcmp(name, "jacobi_transpose")) ctx().jacobi_transpose = (int)value;
     else if (!strcmp(name, "force_unblocked_qr")) ctx().force_unblocked_qr = (int)value;
     else if (!strcmp(name, "no_sketch_cluster")) ctx().no_sketch_cluster = (int)value;
-    else if (!strcmp(name, "sketch_int_widen")) ctx().sketch_int_widen = (int)value;
     else if (!strcmp(name, "qr_blocked_rows")) ctx().qr_blocked_rows = (int)value;
     else if (!strcmp(name, "m_global")) ctx().m_global = value;
     else if (!strcmp(name, "single_device")) g_single_device = (int)value;
