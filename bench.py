@@ -243,8 +243,11 @@ def north_star_records(lib, torch, dist, D, native, rank, world, peak):
         return t.item()
 
     # ---- C5: low_rank_svd_rand_decomp_fixed_rank 1,000,000 x 100,000, k=1000 p=50 q=2 ------------------------------------
+    small = bool(os.environ.get("BENCH_NORTH_STAR_TEST"))      # code-path check on a small box: same calls, reduced shapes
     m, n, k, p, q = C5["rows"], C5["n"], C5["k"], C5["p"], 2
-    l, mg = k + p, C5["rows"] * world
+    if small:
+        m, n = 24000, 20000
+    l, mg = k + p, m * world
     lib.rsvd_b200_set_option(b"row0", rank * m); lib.rsvd_b200_set_option(b"m_global", mg)
     A, _ = gen_lowrank(torch, m, n, 1280, -3.0, 1e-6, 4321, rank, mg)
     U = D.new_cm(m, k); V = D.new_cm(n, k); Sv = torch.empty(k, dtype=torch.float64, device="cuda")
@@ -263,7 +266,7 @@ def north_star_records(lib, torch, dist, D, native, rank, world, peak):
         fn()
         tp = timed(fn)
         passes[name] = {"ms": tp * 1e3, "tflops_per_gpu": 2.0 * m * n * l / tp / 1e12, "frac_of_fp64_peak": 2.0 * m * n * l / tp / 1e12 / peak}
-    out["c5"] = {"workload": C5["workload"], "time_to_solution_s": t, "tflops": flops / t / 1e12,
+    out["c5"] = {"workload": C5["workload"] if not small else "TEST SHAPE %d x %d" % (mg, n), "time_to_solution_s": t, "tflops": flops / t / 1e12,
                  "frac_of_fp64_peak_whole_job": flops / t / 1e12 / (peak * world), "passes": passes, "percent_error": pe,
                  "target": ">= 0.60 of the FP64 roofline per GEMM pass"}
     del A, U, V, Y, Z
@@ -271,6 +274,8 @@ def north_star_records(lib, torch, dist, D, native, rank, world, peak):
 
     # ---- C4: id_two_sided_rand_decomp_fixed_rank + cur_rand_decomp_fixed_rank 400,000 x 50,000, k=1000 p=20 q=2 -----------
     mg, n, k, p = 400000, 50000, 1000, 20
+    if small:
+        mg, n = 48000, 36000
     l = k + p
     r0, m = native.row_partition(mg, world, rank)
     lib.rsvd_b200_set_option(b"row0", r0); lib.rsvd_b200_set_option(b"m_global", mg)
@@ -295,7 +300,7 @@ def north_star_records(lib, torch, dist, D, native, rank, world, peak):
     err_cur = ((As - Cm.t()[rows] @ Um.t() @ Rm.t()).norm() / As.norm()).item()
     opt = (torch.sqrt((sig[k:] ** 2).sum()) / torch.sqrt((sig ** 2).sum())).item()
     id_flops = (1 + 2 * q) * 2.0 * mg * n * l
-    out["c4"] = {"workload": "id_two_sided_rand_decomp_fixed_rank + cur_rand_decomp_fixed_rank 400000x50000 fp64, k=1000 p=20 q=2, row-partitioned x%d (BASELINE configs[3])" % world,
+    out["c4"] = {"workload": "id_two_sided_rand_decomp_fixed_rank + cur_rand_decomp_fixed_rank %dx%d fp64, k=1000 p=20 q=2, row-partitioned x%d (BASELINE configs[3]%s)" % (mg, n, world, ", TEST SHAPE" if small else ""),
                  "id_two_sided_s": t_id, "cur_s": t_cur, "id_gemm_tflops": id_flops / t_id / 1e12,
                  "id_gemm_floor_s": id_flops / (peak * 1e12 * world),
                  "column_id_rel_err_sampled_rows": err_id, "cur_rel_err_sampled_rows": err_cur, "optimal_rank_k_rel_err": opt}
@@ -553,7 +558,7 @@ def main():
         del A_cm
     del U, V
     torch.cuda.empty_cache()
-    if world == 8 and args.config == "c2" and not os.environ.get("BENCH_NO_NORTH_STAR"):
+    if (world == 8 or (world > 1 and os.environ.get("BENCH_NORTH_STAR_TEST"))) and args.config == "c2" and not os.environ.get("BENCH_NO_NORTH_STAR"):
         try:
             north = north_star_records(lib, torch, dist, D, native, rank, world, peak)
         except Exception as exc:     # never lose the main line to the extras

@@ -203,7 +203,11 @@ using namespace rsvd;
 
 extern "C" {
 
-int rsvd_b200_init(int device) { return init_device(device); }
+int rsvd_b200_init(int device) {
+    const int rc = init_device(device);
+    if (!rc) (void)pool_size();      // RSVD_B200_DEVICES: start the workers (and their NCCL ranks) now, not inside the first timed call
+    return rc;
+}
 int rsvd_b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
@@ -343,6 +347,7 @@ int rsvd_b200_d2h(double *h, const double *d, rsvd_i64 n) { return copy_d2h(h, d
 void *rsvd_b200_host_alloc(size_t bytes) {
     ensure_init();
     if (!ctx().inited) return nullptr;
+    (void)pool_size();               // a driver's first large matrix_new is the natural place to bring the worker pool up
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 8, cudaHostAllocPortable) != cudaSuccess) {   // pinned for every device (multi-GPU uploads)
         (void)cudaGetLastError();

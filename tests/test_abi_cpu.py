@@ -87,6 +87,31 @@ def test_no_cpu_fallback_fails_loudly():
     native.dev().rsvd_b200_clear_error()
 
 
+def test_multi_device_request_without_gpus_fails_loudly():
+    """RSVD_B200_DEVICES on a box without GPUs: the worker pool is not created, the error is recorded, hot-path calls still fail
+    loudly (no CPU fallback), the plain-C helpers keep working."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    code = ("import numpy as np, lowrankmatrixdecompositioncodes_b200 as pkg\n"
+            "lib = pkg.native.dev()\n"
+            "assert lib.rsvd_b200_active_devices() == 1\n"
+            "assert lib.rsvd_b200_status() != 0 and b'CUDA device' in lib.rsvd_b200_last_error()\n"
+            "api = pkg.Api(32)\n"
+            "M = api.to_mat(np.arange(12.0).reshape(3, 4))\n"
+            "assert api.lib.get_matrix_frobenius_norm(M) == float(np.linalg.norm(np.arange(12.0)))\n"
+            "try:\n"
+            "    api.svd_rand(np.random.rand(30, 20), 4, 2)\n"
+            "    raise SystemExit('no error raised')\n"
+            "except RuntimeError as e:\n"
+            "    assert 'CUDA device' in str(e) or 'fallback' in str(e), e\n"
+            "print('ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, RSVD_B200_DEVICES="0-3"), timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
 @pytest.mark.parametrize("bits", [32, 64])
 def test_binary_io_both_formats(bits, tmp_path):
     api = pkg.Api(bits)
