@@ -1,6 +1,19 @@
 /* rsvd_b200_rra_decl.h — declarations behind the drop-in header rank_revealing_algorithms_intel_mkl.h
  * (reference: multi_core_mkl_code/rank_revealing_algorithms_intel_mkl.h:3-110 and the _64bit twin).
- * The randomized range-finder / QB hot path is implemented on the B200 (sm_100a); see SURVEY.md §8a. */
+ * The randomized range-finder / QB hot path is implemented on the B200 (sm_100a); see SURVEY.md §8a.
+ *
+ * LIMITS of this build (violations are reported through rsvd_b200_api_status() / rsvd_b200_api_last_error(); outputs are still
+ * allocated, zero-filled, so existing matrix_delete calls stay safe):
+ *   - sketch width k + p <= 2048, and min(m, n) <= 2048 for the full-SVD baseline low_rank_svd_decomp_fixed_rank_or_prec
+ *     (the l x l factor goes through the one-sided Jacobi kernel);
+ *   - k + p <= min(m, n), s > 0 (unchecked undefined behaviour in the reference);
+ *   - several GPUs (RSVD_B200_DEVICES=0-7, or one process per GPU): the hot-path entry points
+ *     low_rank_svd_rand_decomp_fixed_rank, randQB_pb_new, low_rank_svd_blockrand_decomp_fixed_rank_or_prec,
+ *     id_rand_decomp_fixed_rank, id_two_sided_rand_decomp_fixed_rank, cur_rand_decomp_fixed_rank are row-partitioned;
+ *     everything else (deterministic baselines, legacy randomized_low_rank_svd*, randQB_p[b], the block-randomized ID/CUR
+ *     tails, the matrix_vector_functions helpers) runs on ONE device, the first one listed;
+ *   - randQB_pb_new in tolerance mode (nstep <= 0) allocates Q (m x kstep*floor(min(m,n)/kstep)) and B at their maximum size,
+ *     as the reference does (RRA:1607-1609), on the device(s) as well as on the host. */
 #ifndef RSVD_B200_RRA_DECL_H
 #define RSVD_B200_RRA_DECL_H
 

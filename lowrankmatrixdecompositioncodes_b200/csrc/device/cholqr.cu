@@ -333,11 +333,30 @@ void orthonormalize(double *Y, i64 ldy, i64 m, i64 l, double *R, i64 ldr, bool s
                 // triangular solve can produce an orthonormal basis of all l columns.  Last resort = what the reference does
                 // (dgeqrf + dorgqr, MVF:1251-1263): Householder QR with the explicit Q, whose extra columns are an orthonormal
                 // completion.  BLAS-2 speed (one kernel per reflector), only ever reached on singular panels.
+                c.last_qr_path = 3;
                 if (sharded && c.world > 1) {
-                    set_error("rsvd_b200: orthonormalisation failed (row-partitioned panel %lld x %lld is numerically singular)", (long long)m, (long long)l);
+                    // Row-partitioned panel: TSQR with explicit factors.  Y_g = Q_g R_g (local Householder, explicit Q_g), the
+                    // world's R_g are stacked by an all-gather and factored again with an explicit Q_s; Q = Q_g Q_s[g] is
+                    // orthonormal for any rank (Householder completes the basis), R is the factor of the stack.
+                    if (m < l) {
+                        set_error("rsvd_b200: orthonormalisation of a numerically singular row-partitioned panel needs >= %lld rows per rank (this one holds %lld)", (long long)l, (long long)m);
+                        return;
+                    }
+                    const i64 rows = (i64)c.world * l;
+                    DBuf Rg((size_t)l * l), stack((size_t)rows * l), Rs((size_t)l * l), Qg((size_t)m * l), Qs((size_t)l * l);
+                    copy_matrix(Y, ldy, Qg.p, m, m, l);
+                    geqrf_q(Qg.p, m, m, l, Rg.p, l);                          // Qg <- Q_g, Rg <- R_g
+                    DBuf all((size_t)rows * l);
+                    allgather(Rg.p, all.p, (size_t)l * l);                    // [R_0 | R_1 | ...], each l x l column-major
+                    for (int g = 0; g < c.world; ++g) copy_matrix(all.p + (i64)g * l * l, l, stack.p + (i64)g * l, rows, l, l);
+                    geqrf_q(stack.p, rows, rows, l, Rs.p, l);                 // stack <- Q_s (rows x l), Rs <- R
+                    copy_matrix(stack.p + (i64)c.rank * l, rows, Qs.p, l, l, l);
+                    Gemm q3;
+                    q3.ta = 'N'; q3.tb = 'N'; q3.m = m; q3.n = l; q3.k = l; q3.A = Qg.p; q3.lda = m; q3.B = Qs.p; q3.ldb = l; q3.C = Y; q3.ldc = ldy;
+                    gemm(q3);
+                    if (R) copy_matrix(Rs.p, l, R, ldr, l, l);
                     return;
                 }
-                c.last_qr_path = 3;
                 geqrf_q(Y, ldy, m, l, R ? R1.p : nullptr, l);   // Y <- Q, R1 <- R
                 if (R) copy_matrix(R1.p, l, R, ldr, l, l);
                 return;

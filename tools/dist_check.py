@@ -121,6 +121,25 @@ for (m, n, k, p, q, s, spec) in [(2000, 1500, 100, 20, 2, 1, "gap"), (3001, 900,
         d = np.linalg.norm(Qfull @ Bn - Qr @ Br) / np.linalg.norm(A)
         report("randQB kstep=%d nstep=%d tol=%.3g world=%d" % (kstep, nstep, tol, world), f == frr and d < 1e-11, "frank %d (ref %d) ||QB-QrBr||/||A|| %.2e" % (f, frr, d))
 
+# ---- a numerically SINGULAR row-partitioned panel: exact rank 30 sketched with l = 60 columns (TSQR with explicit Q) ----------
+m, n, k, p = 4000, 700, 40, 20
+rng = np.random.default_rng(4)
+A = (np.linalg.qr(rng.standard_normal((m, 30)))[0] * np.logspace(0, -2, 30)) @ np.linalg.qr(rng.standard_normal((n, 30)))[0].T
+r0, rows = native.row_partition(m, world, rank)
+lib.rsvd_b200_set_option(b"row0", r0)
+lib.rsvd_b200_set_option(b"m_global", m)
+A_loc = D.from_numpy_cm(np.ascontiguousarray(A[r0:r0 + rows, :]))
+torch.cuda.synchronize()
+U, S, V = D.svd_rand(A_loc, k, p, 1, 2, 1, seed=777)
+lib.rsvd_b200_sync()
+Ufull, Sn, Vn = gather_rows(U, rows, k), S.cpu().numpy(), D.to_numpy(V)
+strue = np.logspace(0, -2, 30)
+rel = np.max(np.abs(Sn[:30] - strue) / strue)
+e = np.linalg.norm(A - (Ufull * Sn) @ Vn.T) / np.linalg.norm(A)
+report("svd_rand of an exact rank-30 matrix, l=60, world=%d" % world, rel < 1e-10 and Sn[30:].max() < 1e-12 and e < 1e-12 and np.abs(Ufull.T @ Ufull - np.eye(k)).max() < 1e-12,
+       "max rel sigma err (first 30) %.2e  max sigma beyond the rank %.1e  recon %.1e  ||UtU-I|| %.1e  qr path %d" % (
+           rel, Sn[30:].max(), e, np.abs(Ufull.T @ Ufull - np.eye(k)).max(), lib.rsvd_b200_get_option(b"last_qr_path")))
+
 t = torch.tensor([1.0 if ok else 0.0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
