@@ -238,43 +238,57 @@ __global__ void __launch_bounds__(256) qp_wide_kernel(StepP p) {
     const int lane = threadIdx.x & 31;
     const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     Best best; best.v = -2.0; best.pos = 0x7fffffff; best.c = -1;
+    // Software pipeline across columns: the scalars, the F row and the first 128 rows of column c + nw are requested before
+    // column c is reduced, so a warp always has two columns' worth of loads in flight (the sweep is latency-, not issue-bound).
+    struct Pre { double v1, v2, fi, x0, x1, x2, x3; int ps; };
+    auto prefetch = [&](int c) {
+        Pre q;
+        const double *col = p.A + (i64)c * p.lda + k;
+        q.v1 = p.vn1[c]; q.v2 = p.vn2[c]; q.ps = p.pos[c];
+        q.fi = (lane < j) ? p.Ft[(i64)c * QNB + lane] : 0.0;
+        q.x0 = (lane < len) ? col[lane] : 0.0; q.x1 = (lane + 32 < len) ? col[lane + 32] : 0.0;
+        q.x2 = (lane + 64 < len) ? col[lane + 64] : 0.0; q.x3 = (lane + 96 < len) ? col[lane + 96] : 0.0;
+        return q;
+    };
+    Pre cur;
+    if (w0 < p.nloc) cur = prefetch(w0);
     for (int c = w0; c < p.nloc; c += nw) {
-        // every independent load of this column is issued before anything is consumed: one memory latency per column, not five
+        Pre nxt = cur;
+        if (c + nw < p.nloc) nxt = prefetch(c + nw);
+        const double v1 = cur.v1, v2 = cur.v2;
+        const int ps = cur.ps;
+        double fi = cur.fi;
+        double x0 = cur.x0, x1 = cur.x1, x2 = cur.x2, x3 = cur.x3;
+        cur = nxt;
+        if (v1 < 0.0) continue;                                   // already a pivot (warp-uniform)
         double *col = p.A + (i64)c * p.lda + k;
         double *f = p.Ft + (i64)c * QNB;
-        const double v1 = p.vn1[c], v2 = p.vn2[c];
-        const int ps = p.pos[c];
-        double fi = (lane < j) ? f[lane] : 0.0;
-        double dot = 0.0, a0 = 0.0;
-        {
-            int r = lane;
-            double x0 = (r < len) ? col[r] : 0.0, x1 = (r + 32 < len) ? col[r + 32] : 0.0, x2 = (r + 64 < len) ? col[r + 64] : 0.0,
-                   x3 = (r + 96 < len) ? col[r + 96] : 0.0;
-            if (v1 < 0.0) continue;                               // already a pivot (warp-uniform)
-            a0 = x0;
-            for (;;) {
-                const int rn = r + 128;
-                double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
-                if (rn < len) {                                   // next batch in flight while this one is reduced
-                    y0 = col[rn]; y1 = (rn + 32 < len) ? col[rn + 32] : 0.0; y2 = (rn + 64 < len) ? col[rn + 64] : 0.0; y3 = (rn + 96 < len) ? col[rn + 96] : 0.0;
-                }
-                if (r < len) dot = fma(x0, vs[r], dot);
-                if (r + 32 < len) dot = fma(x1, vs[r + 32], dot);
-                if (r + 64 < len) dot = fma(x2, vs[r + 64], dot);
-                if (r + 96 < len) dot = fma(x3, vs[r + 96], dot);
-                if (rn >= len) break;
-                r = rn; x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+        double dot = 0.0;
+        const double a0l = x0;
+        for (int r = lane;;) {
+            const int rn = r + 128;
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+            if (rn < len) {                                       // next batch in flight while this one is reduced
+                y0 = col[rn]; y1 = (rn + 32 < len) ? col[rn + 32] : 0.0; y2 = (rn + 64 < len) ? col[rn + 64] : 0.0; y3 = (rn + 96 < len) ? col[rn + 96] : 0.0;
             }
+            if (r < len) dot = fma(x0, vs[r], dot);
+            if (r + 32 < len) dot = fma(x1, vs[r + 32], dot);
+            if (r + 64 < len) dot = fma(x2, vs[r + 64], dot);
+            if (r + 96 < len) dot = fma(x3, vs[r + 96], dot);
+            if (rn >= len) break;
+            r = rn; x0 = y0; x1 = y1; x2 = y2; x3 = y3;
         }
-        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        a0 = __shfl_sync(0xffffffffu, a0, 0);
-        double corr = fi * auxs[lane];
-        for (int o = 16; o > 0; o >>= 1) corr += __shfl_xor_sync(0xffffffffu, corr, o);
+        // one shuffle tree for the three sums: A(k:m,c)^T v, F(c,0:j) aux and V(k,0:j) F(c,0:j)^T
+        double corr = fi * auxs[lane], rup = (lane < j) ? fi * vrow[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            corr += __shfl_xor_sync(0xffffffffu, corr, o);
+            rup += __shfl_xor_sync(0xffffffffu, rup, o);
+        }
+        const double a0 = __shfl_sync(0xffffffffu, a0l, 0);
         const double fj = fma(tau, dot, corr);                    // F(c, j) = tau A(k:m,c)^T v - tau F(c,0:j) V^T v
         if (lane == j) { fi = fj; f[j] = fj; }
-        double ru = fi * vrow[lane];
-        for (int o = 16; o > 0; o >>= 1) ru += __shfl_xor_sync(0xffffffffu, ru, o);
-        const double akc = a0 - ru;                               // A(k, c) -= V(k, 0:j+1) F(c, 0:j+1)^T
+        const double akc = a0 - (rup + fj);                       // A(k, c) -= V(k, 0:j+1) F(c, 0:j+1)^T   (V(k, j) = 1)
         if (lane == 0) col[0] = akc;
         double vnew = v1;
         if (p.downdate && v1 != 0.0) {
@@ -423,7 +437,9 @@ void qp_factor(double *A, i64 lda, int m, int nloc, int col0, int n_global, bool
     const int world = sharded ? c.world : 1;
     const int kmax = std::min(m, n_global);
     W.kmax = kmax;
-    const int wide_blocks = std::max(1, std::min((nloc + 7) / 8, c.sms * 8));
+    int per_sm = 0;
+    RSVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_wide_kernel, 256, (size_t)(m + 2 * QNB) * sizeof(double)));
+    const int wide_blocks = std::max(1, std::min((nloc + 7) / 8, c.sms * std::max(1, per_sm)));   // one resident wave: no CTA waits for a slot
     W.vn1.alloc((size_t)nloc + 1); W.vn2.alloc((size_t)nloc + 1); W.Ft.alloc((size_t)QNB * nloc + 1);
     W.Vall.alloc((size_t)m * (kmax + QNB)); W.Rpiv.alloc((size_t)kmax * kmax + 1); W.tau.alloc((size_t)kmax + 1); W.aux.alloc(QNB);
     W.vglob.alloc((size_t)m + 1); W.part_v.alloc((size_t)wide_blocks);

@@ -152,3 +152,49 @@ def test_product_and_random_helpers(both):
     assert rel(P0, P1) < 1e-14
     assert np.array_equal(ours.omega(33, 21, seed=4), ref.omega(33, 21, seed=4))
     ours.check()
+
+
+def test_a_failed_helper_call_does_not_poison_the_next_one(both):
+    """The out-of-band error status is sticky inside the device layer; every top-level helper call clears it on entry, so an
+    unmodified C driver that never heard of rsvd_b200_api_clear_error() keeps working after one bad call."""
+    ours, _ = both
+    wide = rng.standard_normal((10, 30))
+    (Qbad,), _ = call(ours, "QR_factorization_getQ", (wide,), [(10, 30)])       # m < n: reported, outputs untouched (zeros)
+    assert ours.lib.rsvd_b200_api_status() != 0 and np.abs(Qbad).max() == 0
+    # no explicit clear: the next helper call starts clean and computes
+    (P,), _ = call(ours, "matrix_matrix_mult", (A, B), [(70, 25)])
+    assert ours.lib.rsvd_b200_api_status() == 0
+    assert rel(P, A @ B) < 1e-14
+    # a composite helper keeps ONE status across its nested calls
+    S = np.diag(np.arange(1.0, 6.0))
+    U5, V5 = np.linalg.qr(rng.standard_normal((20, 5)))[0], np.linalg.qr(rng.standard_normal((12, 5)))[0]
+    (P2,), _ = call(ours, "form_svd_product_matrix", (U5, S, V5), [(20, 12)])
+    ours.check()
+    assert rel(P2, U5 @ S @ V5.T) < 1e-14
+
+
+def test_allocation_helpers_are_thread_safe(both):
+    """Reference drivers call vector_new / vector_delete inside omp parallel loops: the pinned-block tables behind matrix_new
+    are guarded, small allocations never touch them."""
+    import threading
+    ours, _ = both
+    errs = []
+
+    def worker(seed):
+        try:
+            r = np.random.default_rng(seed)
+            for _ in range(200):
+                n = int(r.integers(1, 2000))
+                v = ours.lib.vector_new(n)
+                v.contents.d[n - 1] = 1.0
+                ours.lib.vector_delete(v)
+            for _ in range(3):
+                M = ours.lib.matrix_new(3000, 3000)          # 72 MB: pinned path, goes through the tables
+                M.contents.d[0] = 2.0
+                ours.lib.matrix_delete(M)
+        except Exception as e:     # pragma: no cover
+            errs.append(e)
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(6)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs

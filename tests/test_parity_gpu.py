@@ -192,6 +192,19 @@ def test_blockrand_svd_vs_reference(api, oracle):
 
 
 # ---- ID / CUR ------------------------------------------------------------------------------------------------------
+def test_blockrand_svd_tolerance_mode_when_integer_division_gives_no_blocks(api, oracle):
+    """RRA:251-266: nstep = (k+p)/kstep by C integer division; with k = -1 and p <= kstep it is 0, and randQB_pb_new then runs
+    TOLERANCE-driven — the one way this entry point reaches tolerance mode.  Same frank, sigma, subspaces."""
+    if not hasattr(oracle, "lib"):
+        pytest.skip("needs the compiled reference")
+    A, _ = O.make_matrix(900, 700, "logspace", seed=9)
+    tol = 0.3 * float(np.linalg.norm(A))
+    f, U, S, V = api.svd_blockrand(A, -1, 20, tol, 1, 20, 2, 1, seed=12)
+    fr, Ur, Sr, Vr = oracle.svd_blockrand(A, -1, 20, tol, 1, 20, 2, 1, seed=12)
+    assert f == fr and 0 < f < 700 and S.shape == Sr.shape
+    assert rel_sigma_err(S, Sr) < 1e-10 and subspace_sin(U, Ur) < 1e-6 and subspace_sin(V, Vr) < 1e-6
+
+
 def test_id_cur_vs_golden(api, golden):
     A = golden["A"]
     I, T = api.id_rand(A, 8, 4, 2, 1, seed=777)
