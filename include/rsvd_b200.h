@@ -61,6 +61,10 @@ int rsvd_b200_fill_normal(double *d, rsvd_i64 n, uint64_t seed, rsvd_i64 first);
 /* QR_factorization_getQ / compact_QR_factorization (MVF:1251-1263, 1214-1245; dgeqrf+dorgqr):
  * Y (m x l) <- Q in place; R (l x l upper, may be NULL).  CholeskyQR2, TSQR-preconditioned fallback. */
 int rsvd_b200_orthonormalize(double *Y, rsvd_i64 ldy, rsvd_i64 m, rsvd_i64 l, double *R, rsvd_i64 ldr);
+/* The l x l step of one Cholesky-QR pass (the triangular factor the reference gets from dgeqrf, MVF:1251-1263): G (n x n, upper
+ * triangle read) <- R with G = R^T R (exact zeros below the diagonal), Rinv <- R^{-1}; dminmax (HOST, 2 doubles, may be NULL) =
+ * min / max of diag(R).  Returns 0, the failing column + 1 when G is not positive definite, or -1 on an error. */
+int rsvd_b200_chol_inv(double *G, rsvd_i64 ldg, rsvd_i64 n, double *Rinv, rsvd_i64 ldi, double *dminmax);
 /* pivotedQR_mkl (RRA:924-976; dgeqp3): in place, R in the upper triangle, jpvt 0-based stored as doubles. */
 int rsvd_b200_geqp3(double *A, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n, double *jpvt);
 /* the same followed by dorgqr (RRA:957-964): Q (m x min(m,n)) is formed from the Householder reflectors, orthonormal for any input */

@@ -59,6 +59,17 @@ int rsvd_b200_orthonormalize(double *Y, rsvd_i64 ldy, rsvd_i64 m, rsvd_i64 l, do
     return g_status;
 }
 
+int rsvd_b200_chol_inv(double *G, rsvd_i64 ldg, rsvd_i64 n, double *Rinv, rsvd_i64 ldi, double *dminmax) {
+    READY();
+    int info = ctx().no_chol_dataflow ? -1 : chol_inv_upper(G, ldg, n, Rinv, ldi, dminmax);
+    if (info < 0 && !g_status) {      // per-block launch sequence (option no_chol_dataflow, or no cooperative launch)
+        info = potrf_upper(G, ldg, n);
+        if (info == 0) trtri_upper(G, ldg, n, Rinv, ldi);
+        if (dminmax) dminmax[0] = dminmax[1] = 0.0;
+    }
+    return g_status ? -1 : info;
+}
+
 int rsvd_b200_geqp3(double *A, rsvd_i64 lda, rsvd_i64 m, rsvd_i64 n, double *jpvt) {
     READY();
     geqp3(A, lda, m, n, jpvt);

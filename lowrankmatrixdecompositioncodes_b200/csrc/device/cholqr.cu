@@ -223,16 +223,21 @@ static int cholqr_pass(const double *Yin, i64 ldy, i64 m, i64 l, double *Qout, i
     set_zero(G.p, (size_t)l * l);                         // skipped tiles must not feed NaNs into the all-reduce / trailing updates
     gemm(g);
     if (sharded) allreduce_sum(G.p, (size_t)l * l);
-    int info = potrf_upper(G.p, l, l);
-    if (info != 0) return 1;
-    diag_minmax_kernel<<<1, 256, 0, ctx().stream>>>(G.p, l, l, stat.p);
-    count_launch();
     double h[2];
-    RSVD_CUDA(cudaMemcpyAsync(h, stat.p, 16, cudaMemcpyDeviceToHost, ctx().stream));
-    RSVD_CUDA(cudaStreamSynchronize(ctx().stream));
+    int info = ctx().no_chol_dataflow ? -1 : chol_inv_upper(G.p, l, l, Rinv.p, l, h);   // factor, inverse and diagonal statistics in one kernel
+    if (info > 0 || g_status) return 1;
+    const bool fused = (info == 0);
+    if (!fused) {
+        info = potrf_upper(G.p, l, l);
+        if (info != 0) return 1;
+        diag_minmax_kernel<<<1, 256, 0, ctx().stream>>>(G.p, l, l, stat.p);
+        count_launch();
+        RSVD_CUDA(cudaMemcpyAsync(h, stat.p, 16, cudaMemcpyDeviceToHost, ctx().stream));
+        RSVD_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
     if (ratio_out) *ratio_out = (h[0] > 0.0) ? h[1] / h[0] : INFINITY;
     if (!(h[0] > 0.0) || h[1] / h[0] > cond_limit) return 1;
-    trtri_upper(G.p, l, l, Rinv.p, l);
+    if (!fused) trtri_upper(G.p, l, l, Rinv.p, l);
     Gemm q;   // Qout = Yin * Rinv
     q.ta = 'N'; q.tb = 'N'; q.m = m; q.n = l; q.k = l; q.A = Yin; q.lda = ldy; q.B = Rinv.p; q.ldb = l; q.C = Qout; q.ldc = ldq;
     q.b_upper = true;                                     // trtri_upper leaves exact zeros below the diagonal

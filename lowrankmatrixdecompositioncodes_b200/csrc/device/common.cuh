@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <algorithm>
 
 #include "../../../include/rsvd_b200.h"
 #include "../../../include/rsvd_b200_rng.h"
@@ -51,6 +52,7 @@ struct Ctx {
     int qr_blocked_rows = 2048;      // inputs with at most this many rows go to the blocked pivoted QR (geqp3_blocked.cu)
     int force_unblocked_qr = 0;      // option: pivoted QR through the one-reflector-per-step kernel even for short-wide inputs
     int jacobi_transpose = 0;        // run the one-sided Jacobi on R^T (lower triangular) instead of R
+    int no_chol_dataflow = 0;        // option: l x l Cholesky + inverse through the per-block launch sequence instead of cholinv.cu
     void *staging = nullptr;         // pinned staging buffers of this context (runtime.cu)
     int last_qr_path = 0;            // 1 = CholeskyQR2, 2 = TSQR-preconditioned fallback, 3 = Householder with explicit Q (singular panel)
     unsigned long long qr_fallbacks = 0;
@@ -148,6 +150,10 @@ i64 mgs_rank_estimate(double *Q, i64 ldq, i64 m, i64 maxdim, double tol);       
 void orthonormalize(double *Y, i64 ldy, i64 m, i64 l, double *R, i64 ldr, bool sharded = true, bool loose = false);
 int potrf_upper(double *G, i64 ldg, i64 n);       // in-place upper Cholesky G = R^T R; returns 0 or failing column+1
 void trtri_upper(const double *R, i64 ldr, i64 n, double *Rinv, i64 ldi); // Rinv = R^{-1}
+// cholinv.cu: both in one dataflow kernel.  G <- R (upper, zeros below), Rinv <- R^{-1}; dminmax (host, optional) = min/max diag(R).
+// 0 ok, > 0 failing column + 1, < 0 not run (caller uses the two functions above).  Synchronises the stream.
+bool chol_inv_ok(i64 n);
+int chol_inv_upper(double *G, i64 ldg, i64 n, double *Rinv, i64 ldi, double *dminmax);
 
 // ---- Householder QR family (geqp3.cu) ----------------------------------------------------------
 // In-place dgeqp3-compatible column-pivoted QR (R in the upper triangle, jpvt 0-based as doubles).

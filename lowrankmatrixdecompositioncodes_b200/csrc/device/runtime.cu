@@ -228,6 +228,7 @@ void rsvd_b200_set_option(const char *name, rsvd_i64 value) {
     else if (!strcmp(name, "force_qr_fallback")) ctx().force_qr_fallback = (int)value;
     else if (!strcmp(name, "row0")) ctx().row0 = value;
     else if (!strcmp(name, "jacobi_transpose")) ctx().jacobi_transpose = (int)value;
+    else if (!strcmp(name, "no_chol_dataflow")) ctx().no_chol_dataflow = (int)value;
     else if (!strcmp(name, "force_unblocked_qr")) ctx().force_unblocked_qr = (int)value;
     else if (!strcmp(name, "no_sketch_cluster")) ctx().no_sketch_cluster = (int)value;
     else if (!strcmp(name, "qr_blocked_rows")) ctx().qr_blocked_rows = (int)value;

@@ -46,6 +46,7 @@ SIGNATURES = {
     "rsvd_b200_sketch": (C.c_int, [C.c_char, i64, i64, i64, dp, i64, u64, i64, i64, i64, dp, i64]),
     "rsvd_b200_fill_normal": (C.c_int, [dp, i64, u64, i64]),
     "rsvd_b200_orthonormalize": (C.c_int, [dp, i64, i64, i64, dp, i64]),
+    "rsvd_b200_chol_inv": (C.c_int, [dp, i64, i64, dp, i64, dp]),
     "rsvd_b200_geqp3": (C.c_int, [dp, i64, i64, i64, dp]),
     "rsvd_b200_geqp3_q": (C.c_int, [dp, i64, i64, i64, dp, dp, i64]),
     "rsvd_b200_svd_small": (C.c_int, [dp, i64, i64, dp, i64, dp, dp, i64]),

@@ -14,6 +14,8 @@ A_cm += 1e-6 * torch.randn((n, m), dtype=torch.float64, device="cuda", generator
 del X, W
 torch.cuda.synchronize()
 D.svd_rand(A_cm, k, p, 1, 2, 1, seed=777); lib.rsvd_b200_sync()
+if os.environ.get("RSVD_B200_VERBOSE"):      # 3 = per-phase CUDA-event times on stderr (pipeline.cu: Phase)
+    lib.rsvd_b200_set_option(b"verbose", int(os.environ["RSVD_B200_VERBOSE"]))
 torch.cuda.cudart().cudaProfilerStart()
 D.svd_rand(A_cm, k, p, 1, 2, 1, seed=777); lib.rsvd_b200_sync()
 torch.cuda.cudart().cudaProfilerStop()
