@@ -35,6 +35,9 @@ struct Ctx {
     int sms = 148;
     cudaStream_t stream = nullptr;   // compute stream (all kernels)
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;   // side stream for kernels that run next to the compute stream (Jacobi's live replay of V)
+    cudaEvent_t aux_ev[2] = {nullptr, nullptr};
+    int no_live_replay = 0;          // option: rebuild V after the Jacobi kernel has finished instead of next to it
     bool inited = false;
     int *d_flag = nullptr;           // device int[8] scratch for status flags
     int *h_flag = nullptr;           // pinned mirror

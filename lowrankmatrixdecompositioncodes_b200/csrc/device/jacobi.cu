@@ -12,6 +12,7 @@
 // one kernel launch per step (~4.3 us in a CUDA graph: 519 steps x 9 sweeps at l = 520).  A graph-replayed per-step kernel
 // (plain column pairs, V rotated in place, n <= 1280) remains as the fallback when a cooperative launch is not possible.
 #include "common.cuh"
+#include <time.h>
 #include <algorithm>
 #include <vector>
 
@@ -201,6 +202,7 @@ __device__ __forceinline__ void block_sumK(double (&v)[K], double *sh) {   // sh
 }
 
 // ctl[0] = barrier counter, ctl[1] = error flag, ctl[2] = sweeps done, ctl[8 + s] = CTAs that rotated in sweep s,
+// ctl[64] = steps whose log entries are complete (after every round), ctl[65] = total steps + 1 once the kernel is done, ctl[66] = live replay gave up,
 // (unsigned long long *)(ctl + 4)[0] = bit pattern of the largest |cosine| met in the current sweep (positive doubles order like integers)
 // The rotations are only LOGGED (rotlog[step][slot] = (c, s), identity when nothing was rotated): V is rebuilt afterwards by
 // jacobi_replay_kernel, off the critical path.  NT threads per CTA, RPT rows per thread (NT*RPT >= n).
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(NT) jacobi_persistent_kernel(double *G, i64 ld
     __shared__ double sh[2][2 * BW * (NT / 32)];
     const int N = NBk * BW, half = N / 2;
     int gen = 0, shb = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); reinterpret_cast<unsigned long long *>(ctl)[36] = t; }
     unsigned long long *maxcos = reinterpret_cast<unsigned long long *>(ctl + 4);
     i64 gs = 0;      // global step index
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
@@ -304,6 +307,8 @@ __global__ void __launch_bounds__(NT) jacobi_persistent_kernel(double *G, i64 ld
                 atomicMax(maxcos + (sweep & 1), (unsigned long long)__double_as_longlong(cmax));
             }
             if (!grid_barrier(ctl, gen++, ctl + 1)) return;
+            // every CTA's log entries of this round are visible to CTA 0 now: publish the step count for the live replay
+            if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ctl + 64), "r"((int)gs) : "memory");
         }
         const int nrot = *((volatile int *)(ctl + 8 + sweep));
         const double swept = __longlong_as_double((long long)*((volatile unsigned long long *)(maxcos + (sweep & 1))));
@@ -312,6 +317,10 @@ __global__ void __launch_bounds__(NT) jacobi_persistent_kernel(double *G, i64 ld
         // largest SQUARED cosine): Jacobi converges quadratically, so the rotations just applied leave cosines of order 1e-16
         // and the confirming sweep is skipped.
         if (nrot == 0 || swept <= 1.0e-16) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); reinterpret_cast<unsigned long long *>(ctl)[37] = t;
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ctl + 65), "r"((int)gs + 1) : "memory");   // done: steps + 1
     }
 }
 
@@ -373,12 +382,108 @@ __global__ void __launch_bounds__(RR == 4 ? 608 : 1024) jacobi_replay_kernel(dou
     }
 }
 
+
+// The same replay running NEXT TO the Jacobi kernel on a side stream: it follows the published step count (ctl[64]) chunk by
+// chunk, so V is complete a few microseconds after the last rotation instead of 1.8 ms later (l = 520; 4.5 ms on a 20-sweep
+// matrix).  The Jacobi CTAs are latency-bound, so the replay's shared-memory work mostly fits into the issue slots they leave:
+// measured, the Jacobi kernel slows down by 8 % (18.25 -> 19.7 ms over 20 sweeps) and the call gains 2.9 ms net.
+// Two things the hardware insists on (both measured): a cooperative launch runs exclusively, so next to a live replay the
+// Jacobi grid is launched the ordinary way; and CTAs of kernels with different L1/shared-memory carve-outs do not share an
+// SM, so both kernels ask for the same one.  Bounded polling: if no progress arrives the kernel flags ctl[66] and leaves V
+// untouched; the host then replays after the fact.
+template <int RR, int BW>
+__global__ void __launch_bounds__(RR == 4 ? 608 : 1024) jacobi_replay_live_kernel(double *V, i64 ldv, int n, int NBk, const double2 *rotlog,
+                                                                                  int *ctl) {
+    extern __shared__ __align__(16) double T[];          // [N][RR]
+    __shared__ int sh_avail, sh_done;
+    const int N = NBk * BW, half = N / 2;
+    const int r0 = blockIdx.x * RR;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); reinterpret_cast<unsigned long long *>(ctl)[38] = t; }
+    for (int e = threadIdx.x; e < N * RR; e += blockDim.x) {
+        const int col = e / RR, rr = e % RR;
+        T[e] = (col == r0 + rr) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int slot = threadIdx.x;
+    const bool active = slot < half;
+    const int ci = slot / BW, cj = slot % BW;
+    const double2 ident = make_double2(1.0, 0.0);
+    int st = 0, avail = 0;
+    bool final = false;
+    for (int base = 0;; base += RPB) {
+        if (!final && avail < base + RPB) {
+            if (threadIdx.x == 0) {
+                int a = 0, d = 0;
+                long long spins = 0;
+                // sparse relaxed polling (one 8-byte L2 read per CTA every ~2 us: a chunk of RPB steps takes the Jacobi kernel ~14 us),
+                // then one acquire load of the same words orders the log reads behind the publication
+                for (;;) {
+                    a = *((volatile int *)(ctl + 64)); d = *((volatile int *)(ctl + 65));
+                    if (d != 0 || a >= base + RPB) break;
+                    if ((++spins & 15) == 0 && (*((volatile int *)(ctl + 1)) || spins > (1ll << 21))) { ctl[66] = 1; d = -1; break; }
+                    __nanosleep(2000);
+                }
+                if (d >= 0) {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(d) : "l"(ctl + 65) : "memory");
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(a) : "l"(ctl + 64) : "memory");
+                }
+                sh_avail = a; sh_done = d;
+            }
+            __syncthreads();
+            const int d = sh_done;
+            if (d < 0) return;
+            if (d > 0) { final = true; avail = d - 1; } else avail = sh_avail;
+            __syncthreads();
+        }
+        if (base >= avail) { if (final) break; else continue; }
+        const int ns = min(RPB, avail - base);
+        double2 cur[RPB];
+#pragma unroll
+        for (int b = 0; b < RPB; ++b) cur[b] = (active && b < ns) ? __ldcg(rotlog + (i64)(base + b) * half + slot) : ident;
+#pragma unroll
+        for (int b = 0; b < RPB; ++b) {
+            if (b < ns) {                     // uniform
+                if (cur[b].y != 0.0) {
+                    int p, q;
+                    pair_at<BW>(NBk, st, ci, cj, p, q);
+                    double2 *tp = reinterpret_cast<double2 *>(T + p * RR), *tq = reinterpret_cast<double2 *>(T + q * RR);
+                    const double cs = cur[b].x, sn = cur[b].y;
+#pragma unroll
+                    for (int h = 0; h < RR / 2; ++h) {
+                        const double2 x = tp[h], y = tq[h];
+                        tp[h] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
+                        tq[h] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
+                    }
+                }
+                if (++st == N - 1) st = 0;
+                __syncthreads();
+            }
+        }
+        if (ns < RPB) base -= RPB - ns;       // a partial chunk (only at a round boundary or at the end): resume right after it
+    }
+    for (int e = threadIdx.x; e < n * RR; e += blockDim.x) {
+        const int col = e / RR, rr = e % RR;
+        if (r0 + rr < n) V[(i64)col * ldv + r0 + rr] = T[e];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); reinterpret_cast<unsigned long long *>(ctl)[39] = t; }
+}
+
 template <int RR, int BW>
 static void launch_replay(double *V, i64 ldv, int n, int NBk, i64 steps, const double2 *rotlog, cudaStream_t st) {
     const int N = NBk * BW;
     const size_t smem = (size_t)N * RR * sizeof(double);
     RSVD_CUDA(cudaFuncSetAttribute(jacobi_replay_kernel<RR, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     jacobi_replay_kernel<RR, BW><<<(n + RR - 1) / RR, (N / 2 + 31) / 32 * 32, smem, st>>>(V, ldv, n, NBk, steps, rotlog);
+}
+template <int RR, int BW>
+static void launch_replay_live(double *V, i64 ldv, int n, int NBk, const double2 *rotlog, int *ctl, cudaStream_t st) {
+    const int N = NBk * BW;
+    const size_t smem = (size_t)N * RR * sizeof(double);
+    RSVD_CUDA(cudaFuncSetAttribute(jacobi_replay_live_kernel<RR, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // same L1 / shared-memory split as the Jacobi kernel (run_persistent sets it too): an SM cannot host CTAs of two kernels
+    // that ask for different carve-outs, and the replay CTAs would pile up on the SMs the Jacobi grid leaves free
+    RSVD_CUDA(cudaFuncSetAttribute(jacobi_replay_live_kernel<RR, BW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    jacobi_replay_live_kernel<RR, BW><<<(n + RR - 1) / RR, (N / 2 + 31) / 32 * 32, smem, st>>>(V, ldv, n, NBk, rotlog, ctl);
 }
 
 // one (BW, RPT) instantiation of the persistent path; returns sweeps, -1 on a barrier time-out, -2 when it could not launch
@@ -393,26 +498,58 @@ static int run_persistent(double *G, i64 ldg, double *V, i64 ldv, int n, double 
     const int grid = std::min(NBk / 2, blocks_per_sm * c.sms);
     const size_t log_entries = (size_t)max_sweeps * (N - 1) * half;
     if (log_entries * sizeof(double2) > ((size_t)3 << 30)) return -2;
-    int *ctl = (int *)dalloc_bytes(64 * sizeof(int));
+    int *ctl = (int *)dalloc_bytes(128 * sizeof(int));
     double2 *rotlog = (double2 *)dalloc_bytes(log_entries * sizeof(double2));
     if (g_status) return -2;
-    RSVD_CUDA(cudaMemsetAsync(ctl, 0, 64 * sizeof(int), c.stream));
+    RSVD_CUDA(cudaMemsetAsync(ctl, 0, 128 * sizeof(int), c.stream));
+    // live replay: ONE replay CTA per SM at most (66 registers x <= 320 threads next to one 104-register Jacobi CTA) follows the
+    // rotation log from a side stream.  A replay CTA that cannot become resident while the Jacobi kernel runs would only start
+    // afterwards and replay the whole log alone (measured: +8 ms), hence the one-wave condition.
+    const bool live = !c.no_live_replay && c.aux_stream && (n + 3) / 4 <= c.sms && grid <= c.sms;
+    if (live) RSVD_CUDA(cudaEventRecord(c.aux_ev[0], c.stream));
     int ms = max_sweeps;
     void *args[] = {&G, &ldg, (void *)&n, &NBk, (void *)&tol, &ms, &ctl, &rotlog};
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)jacobi_persistent_kernel<BW, RPT, NT>, dim3(grid), dim3(NT), args, 0, c.stream);
+    // A cooperative launch runs exclusively (the side-stream kernel would only start when it has finished — measured), so
+    // next to a live replay the grid is launched the ordinary way: it is no larger than one wave (grid <= blocks_per_sm * SMs,
+    // the replay CTAs fit beside it) and the barrier's bounded spin turns a grid that is not co-resident into an error.
+    cudaError_t e;
+    if (live) {
+        RSVD_CUDA(cudaFuncSetAttribute(jacobi_persistent_kernel<BW, RPT, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        jacobi_persistent_kernel<BW, RPT, NT><<<grid, NT, 0, c.stream>>>(G, ldg, n, NBk, tol, ms, ctl, rotlog);
+        e = cudaGetLastError();
+    } else {
+        e = cudaLaunchCooperativeKernel((void *)jacobi_persistent_kernel<BW, RPT, NT>, dim3(grid), dim3(NT), args, 0, c.stream);
+    }
     int sweeps = -2;
     if (e == cudaSuccess) {
         count_launch();
+        if (live) {
+            RSVD_CUDA(cudaStreamWaitEvent(c.aux_stream, c.aux_ev[0], 0));
+            launch_replay_live<4, BW>(V, ldv, n, NBk, rotlog, ctl, c.aux_stream);
+            count_launch();
+            RSVD_CUDA(cudaEventRecord(c.aux_ev[1], c.aux_stream));
+            RSVD_CUDA(cudaStreamWaitEvent(c.stream, c.aux_ev[1], 0));
+        }
         RSVD_CUDA(cudaMemcpyAsync(c.h_flag + 16, ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        RSVD_CUDA(cudaMemcpyAsync(c.h_flag + 20, ctl + 66, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
         RSVD_CUDA(cudaStreamSynchronize(c.stream));
+        if (c.verbose && live) {
+            unsigned long long ts[4];
+            RSVD_CUDA(cudaMemcpy(ts, ctl + 72, sizeof(ts), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[rsvd_b200] jacobi kernel %.3f ms; live replay started %+.3f ms after it, ended %+.3f ms after its end\n",
+                    (ts[1] - ts[0]) * 1e-6, ((double)ts[2] - (double)ts[0]) * 1e-6, ((double)ts[3] - (double)ts[1]) * 1e-6);
+        }
         if (c.h_flag[17]) { set_error("rsvd_b200: Jacobi device-wide barrier timed out"); sweeps = -1; }
         else {
             sweeps = c.h_flag[18];
             const i64 steps = (i64)sweeps * (N - 1);
-            if (n <= 1184) launch_replay<4, BW>(V, ldv, n, NBk, steps, rotlog, c.stream);   // <= 2 CTAs per SM, one wave
-            else launch_replay<8, BW>(V, ldv, n, NBk, steps, rotlog, c.stream);
-            count_launch();
-            if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d (persistent, %d columns per CTA)\n", n, sweeps, 2 * BW);
+            if (!live || c.h_flag[20]) {      // after the fact (large n, option, or the live replay saw no progress and gave up)
+                if (n <= 1184) launch_replay<4, BW>(V, ldv, n, NBk, steps, rotlog, c.stream);   // <= 2 CTAs per SM, one wave
+                else launch_replay<8, BW>(V, ldv, n, NBk, steps, rotlog, c.stream);
+                count_launch();
+            }
+            if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d (persistent, %d columns per CTA%s)\n", n, sweeps, 2 * BW,
+                                   live ? (c.h_flag[20] ? ", live replay gave up" : ", live replay") : "");
         }
     } else {
         (void)cudaGetLastError();
@@ -503,13 +640,16 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
 
 }  // namespace
 
+static double host_now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + 1e-6 * ts.tv_nsec; }
 void jacobi_svd(double *A, i64 lda, i64 n_, double *U, i64 ldu, double *s, double *Vt, i64 ldvt) {
     ensure_init();
     Ctx &c = ctx();
     const int n = (int)n_;
     if (n <= 0) return;
+    const double t0 = host_now();
     DBuf V((size_t)n * n), sigma((size_t)n);
     if (jacobi_core(A, lda, V.p, n, n) < 0) return;
+    const double t1 = host_now();
     colnorm_kernel<<<(n * 32 + 255) / 256, 256, 0, c.stream>>>(A, lda, n, sigma.p);
     count_launch();
     std::vector<double> hs(n);
@@ -524,6 +664,7 @@ void jacobi_svd(double *A, i64 lda, i64 n_, double *U, i64 ldu, double *s, doubl
     count_launch();
     RSVD_CUDA(cudaStreamSynchronize(c.stream));   // perm (host vector) must outlive the copy
     dfree(dperm);
+    if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi_svd host time: core %.3f ms, sort + finalize %.3f ms\n", t1 - t0, host_now() - t1);
 }
 
 // ---- symmetric eigenproblem (dsyev 'V','U' of MVF:1206-1209, called on B*B^T at RRA:190) -------------------------------

@@ -65,6 +65,8 @@ int init_ctx(Ctx &c, int device) {
     c.sms = prop.multiProcessorCount;
     RSVD_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     RSVD_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    RSVD_CUDA(cudaStreamCreateWithFlags(&c.aux_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) RSVD_CUDA(cudaEventCreateWithFlags(&c.aux_ev[i], cudaEventDisableTiming));
     // keep freed blocks in the pool: cudaMallocAsync then costs microseconds, not a driver round trip
     cudaMemPool_t pool;
     RSVD_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -229,6 +231,7 @@ void rsvd_b200_set_option(const char *name, rsvd_i64 value) {
     else if (!strcmp(name, "row0")) ctx().row0 = value;
     else if (!strcmp(name, "jacobi_transpose")) ctx().jacobi_transpose = (int)value;
     else if (!strcmp(name, "no_chol_dataflow")) ctx().no_chol_dataflow = (int)value;
+    else if (!strcmp(name, "no_live_replay")) ctx().no_live_replay = (int)value;
     else if (!strcmp(name, "force_unblocked_qr")) ctx().force_unblocked_qr = (int)value;
     else if (!strcmp(name, "no_sketch_cluster")) ctx().no_sketch_cluster = (int)value;
     else if (!strcmp(name, "qr_blocked_rows")) ctx().qr_blocked_rows = (int)value;
