@@ -180,6 +180,72 @@ def test_jacobi_svd_and_eig(lib, n):
     assert np.linalg.norm(S @ Vn - Vn * wn) / np.linalg.norm(S) < 1e-12
 
 
+@pytest.mark.parametrize("n", [2, 64, 130, 520, 592, 700])
+def test_jacobi_live_replay_is_bitwise_the_after_the_fact_replay(lib, n):
+    """V rebuilt by the replay kernel that runs NEXT TO the Jacobi kernel (side stream, follows the rotation log as it is
+    written; n <= 4 * SMs) equals the replay launched after the Jacobi kernel has finished, bit for bit."""
+    rng = np.random.default_rng(100 + n)
+    U0, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    V0, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    R = np.triu(np.linalg.qr((U0 * np.logspace(1, -2.5, n)) @ V0.T)[1])
+    out = []
+    for no_live in (0, 1):
+        lib.rsvd_b200_set_option(b"no_live_replay", no_live)
+        Ad = D.from_numpy_cm(R)
+        U = torch.empty((n, n), dtype=torch.float64, device="cuda")
+        Vt = torch.full((n, n), float("nan"), dtype=torch.float64, device="cuda")
+        s = torch.empty(n, dtype=torch.float64, device="cuda")
+        native.check(lib.rsvd_b200_svd_small(Ad.data_ptr(), n, n, U.data_ptr(), n, s.data_ptr(), Vt.data_ptr(), n))
+        sync(lib)
+        out.append((U.t().cpu().numpy(), s.cpu().numpy(), Vt.t().cpu().numpy()))
+    lib.rsvd_b200_set_option(b"no_live_replay", 0)
+    (U1, s1, V1), (U2, s2, V2) = out
+    assert np.array_equal(V1, V2) and np.array_equal(s1, s2) and np.array_equal(U1, U2)
+    assert np.linalg.norm((U1 * s1) @ V1 - R) / np.linalg.norm(R) < 1e-13
+    assert np.abs(V1 @ V1.T - np.eye(n)).max() < 1e-13
+
+
+@pytest.mark.parametrize("n,cond", [(1, 1.0), (5, 10.0), (32, 1e3), (33, 1e3), (100, 1e3), (520, 1e3), (520, 1e6), (545, 1e2), (1050, 1e3),
+                                    (2100, 1e2)])
+def test_cholesky_dataflow_kernel(lib, n, cond):
+    """cholinv.cu: G = R^T R and R^{-1} in one dataflow kernel (32 x 32 block tasks) against numpy, next to the per-block launch
+    sequence it replaces.  Only the upper triangle of G may be read (the lower one is NaN here); both outputs carry exact
+    zeros below the diagonal (the streaming GEMM's triangular hint relies on them)."""
+    import ctypes as C
+    rng = np.random.default_rng(n)
+    Y = rng.standard_normal((max(2 * n, 64), n)) * np.logspace(0, -np.log10(cond), n)
+    G = Y.T @ Y
+    Rref = np.linalg.cholesky(G).T
+    for no_dataflow in (0, 1):
+        lib.rsvd_b200_set_option(b"no_chol_dataflow", no_dataflow)
+        Gd = D.from_numpy_cm(np.triu(G) + np.tril(np.full((n, n), np.nan), -1))
+        Xd = torch.full((n, n), float("nan"), dtype=torch.float64, device="cuda")
+        mm = (C.c_double * 2)()
+        info = lib.rsvd_b200_chol_inv(D.ptr(Gd), n, n, D.ptr(Xd), n, mm)
+        sync(lib)
+        R, X = D.to_numpy(Gd), D.to_numpy(Xd)
+        assert info == 0
+        assert np.all(np.tril(R, -1) == 0) and np.all(np.tril(X, -1) == 0)
+        assert np.abs(R - Rref).max() / np.abs(Rref).max() < 1e-12 * max(1.0, cond / 1e3)
+        assert np.abs(R @ X - np.eye(n)).max() < 1e-12 * cond
+        if not no_dataflow:
+            d = np.diag(Rref)
+            assert abs(mm[0] - d.min()) <= 1e-10 * d.max() and abs(mm[1] - d.max()) <= 1e-10 * d.max()
+    lib.rsvd_b200_set_option(b"no_chol_dataflow", 0)
+
+
+def test_cholesky_dataflow_kernel_reports_the_failing_column(lib):
+    n = 200
+    A = np.eye(n)
+    A[150, 150] = -1.0
+    for no_dataflow in (0, 1):
+        lib.rsvd_b200_set_option(b"no_chol_dataflow", no_dataflow)
+        Gd, Xd = D.from_numpy_cm(A), D.new_cm(n, n)
+        assert lib.rsvd_b200_chol_inv(D.ptr(Gd), n, n, D.ptr(Xd), n, None) == 151
+    lib.rsvd_b200_set_option(b"no_chol_dataflow", 0)
+    native.check(lib.rsvd_b200_sync())
+
+
 @pytest.mark.parametrize("m,n", [(12, 40), (120, 1500), (100, 2000), (300, 5000), (40, 40), (7, 3), (200, 9000), (1500, 400), (2500, 2500)])
 def test_geqp3_pivots_bit_exact_vs_lapack(lib, m, n):
     from scipy.linalg import lapack
