@@ -37,6 +37,8 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t aux_stream = nullptr;   // side stream for kernels that run next to the compute stream (Jacobi's live replay of V)
     cudaEvent_t aux_ev[2] = {nullptr, nullptr};
+    void *block_cache = nullptr;     // runtime.cu: freed work buffers kept for the next request of the same size
+    int no_block_cache = 0;          // option: every dfree goes straight back to the stream-ordered pool
     int no_live_replay = 0;          // option: rebuild V after the Jacobi kernel has finished instead of next to it
     bool inited = false;
     int *d_flag = nullptr;           // device int[8] scratch for status flags
@@ -57,7 +59,7 @@ struct Ctx {
     int jacobi_transpose = 0;        // run the one-sided Jacobi on R^T (lower triangular) instead of R
     int no_chol_dataflow = 0;        // option: l x l Cholesky + inverse through the per-block launch sequence instead of cholinv.cu
     void *staging = nullptr;         // pinned staging buffers of this context (runtime.cu)
-    int last_qr_path = 0;            // 1 = CholeskyQR2, 2 = TSQR-preconditioned fallback, 3 = Householder with explicit Q (singular panel)
+    int last_qr_path = 0;            // 1 = CholeskyQR2, 4 = shifted CholeskyQR3, 2 = TSQR-preconditioned fallback, 3 = Householder with explicit Q (singular panel)
     unsigned long long qr_fallbacks = 0;
 };
 Ctx &ctx();                          // the calling thread's context (primary context unless a worker bound its own)
@@ -68,6 +70,7 @@ void ensure_init();
 double *dalloc(size_t n_doubles);
 void *dalloc_bytes(size_t bytes);
 void dfree(void *p);
+void release_cached_blocks();              // return the calling context's cached work buffers to the pool
 extern unsigned long long g_launches;            // all contexts together (approximate under concurrent workers: statistics only)
 inline void count_launch(int n = 1) { ctx().launches += (unsigned long long)n; __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 

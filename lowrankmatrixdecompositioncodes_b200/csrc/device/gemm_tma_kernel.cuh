@@ -423,6 +423,31 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         } else {
             const double alpha = p.alpha, beta = p.beta;
             double ss = 0.0;          // fused Frobenius norm of the updated C (randQB_pb_new: ||A - Qp Bp||_F, RRA:1750-1751,1771)
+            if (!A_KMAJOR && beta != 0.0 && p.c_vec2 && m0 + BM <= p.m && n0 + 8 * NB <= p.n) {
+                // Read-modify-write of a full interior tile (the rank-kstep update A -= Qp Bp, RRA:1750, has only ~13 k-iterations
+                // per tile, so its epilogue is a third of the work).  Old and new C alias, so the compiler keeps every load behind
+                // the previous store: 32 dependent DRAM round trips per thread.  Here the loads of four column groups are issued
+                // together (8 double2 in flight per thread: 4 round trips per tile instead of 32).
+#pragma unroll
+                for (int nb0 = 0; nb0 < NB; nb0 += 4) {
+                    double2 o[4][2];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc)
+                            if (nb0 + i < NB)
+                                o[i][cc] = __ldcs(reinterpret_cast<const double2 *>(p.C + (n0 + (nb0 + i) * 8 + t + 4 * cc) * p.ldc + m0 + cw * 16 + 2 * g));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc)
+                            if (nb0 + i < NB) {
+                                double2 v = make_double2(fma(beta, o[i][cc].x, alpha * acc[0][nb0 + i][cc]), fma(beta, o[i][cc].y, alpha * acc[1][nb0 + i][cc]));
+                                *reinterpret_cast<double2 *>(p.C + (n0 + (nb0 + i) * 8 + t + 4 * cc) * p.ldc + m0 + cw * 16 + 2 * g) = v;
+                                ss = fma(v.x, v.x, fma(v.y, v.y, ss));
+                            }
+                }
+            } else
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb)
 #pragma unroll

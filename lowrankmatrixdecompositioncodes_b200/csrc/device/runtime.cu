@@ -3,6 +3,9 @@
 // cuBLAS build re-uploads both operands on EVERY GEMM call, matrix_vector_functions_mkl_and_cublas.c:566-577);
 // here one upload per API call keeps A resident for all 2q passes.
 #include "common.cuh"
+#include <mutex>
+#include <unordered_map>
+#include <time.h>
 #include <algorithm>
 #include <stdarg.h>
 #include <mutex>
@@ -91,23 +94,107 @@ void ensure_init() {
     else cudaSetDevice(ctx().device);
 }
 
+// ---- device memory ---------------------------------------------------------------------------------------------------
+// cudaMallocAsync / cudaFreeAsync on the context's stream, with a small per-context cache of freed work buffers on top.
+// Why the cache: the stream-ordered pool usually answers in microseconds, but now and then it goes back to the driver for
+// fresh memory — measured on the 100000 x 50000 blocked QB: single cudaMallocAsync calls of a 153 MB panel buffer taking
+// 18, 39, 59 ms on the host, and 100-700 ms holes in the GPU timeline when such a call fell between two short kernels.  The
+// algorithms ask for the same few sizes over and over (m x l panels, l x l blocks), so a freed block of 1 MB .. 2 GB is kept
+// (up to 6 GB per context, oldest dropped first) and handed to the next request of (nearly) the same size.  Reuse is safe
+// because both uses are ordered on the same stream — exactly the guarantee cudaFreeAsync/cudaMallocAsync give themselves.
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::unordered_map<void *, size_t> live;                 // blocks handed out by this context
+    std::vector<std::pair<void *, size_t>> idle;             // freed, reusable (oldest first)
+    size_t idle_bytes = 0;
+};
+constexpr size_t kCacheMin = (size_t)1 << 20, kCacheMax = (size_t)2 << 30, kCacheTotal = (size_t)6 << 30;
+BlockCache *cache_of(Ctx &c) {
+    if (!c.block_cache) c.block_cache = new BlockCache();
+    return (BlockCache *)c.block_cache;
+}
+void cache_flush(Ctx &c) {
+    BlockCache *bc = cache_of(c);
+    std::lock_guard<std::mutex> lk(bc->mu);
+    for (auto &b : bc->idle) cudaFreeAsync(b.first, c.stream);
+    bc->idle.clear();
+    bc->idle_bytes = 0;
+}
+}  // namespace
+
 void *dalloc_bytes(size_t bytes) {
     ensure_init();
-    if (!ctx().inited) return nullptr;
+    Ctx &c = ctx();
+    if (!c.inited) return nullptr;
     void *p = nullptr;
     if (bytes == 0) bytes = 8;
-    cudaError_t e = cudaMallocAsync(&p, bytes, ctx().stream);
+    BlockCache *bc = cache_of(c);
+    if (bytes >= kCacheMin && bytes <= kCacheMax) {
+        std::lock_guard<std::mutex> lk(bc->mu);
+        for (size_t i = bc->idle.size(); i-- > 0;) {           // newest first
+            const size_t sz = bc->idle[i].second;
+            if (sz >= bytes && sz - bytes <= bytes / 8) {
+                p = bc->idle[i].first;
+                bc->idle_bytes -= sz;
+                bc->idle.erase(bc->idle.begin() + (long)i);
+                bc->live[p] = sz;
+                return p;
+            }
+        }
+    }
+    struct timespec t0, t1;
+    const bool timed = c.verbose != 0;
+    if (timed) clock_gettime(CLOCK_MONOTONIC, &t0);
+    cudaError_t e = cudaMallocAsync(&p, bytes, c.stream);
+    if (e != cudaSuccess) {                                  // give the cached blocks back and try once more
+        (void)cudaGetLastError();
+        cache_flush(c);
+        cudaStreamSynchronize(c.stream);
+        e = cudaMallocAsync(&p, bytes, c.stream);
+    }
+    if (timed) {
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        const double ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+        if (ms > 2.0) fprintf(stderr, "[rsvd_b200] cudaMallocAsync of %.1f MB took %.1f ms on the host\n", bytes / 1048576.0, ms);
+    }
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         set_error("rsvd_b200: device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         return nullptr;
     }
+    if (bytes >= kCacheMin && bytes <= kCacheMax) {
+        std::lock_guard<std::mutex> lk(bc->mu);
+        bc->live[p] = bytes;
+    }
     return p;
 }
 double *dalloc(size_t n) { return (double *)dalloc_bytes(n * sizeof(double)); }
 void dfree(void *p) {
-    if (p) RSVD_CUDA(cudaFreeAsync(p, ctx().stream));
+    if (!p) return;
+    Ctx &c = ctx();
+    BlockCache *bc = cache_of(c);
+    {
+        std::lock_guard<std::mutex> lk(bc->mu);
+        auto it = bc->live.find(p);
+        if (it != bc->live.end()) {
+            const size_t sz = it->second;
+            bc->live.erase(it);
+            if (!c.no_block_cache) {
+                bc->idle.push_back({p, sz});
+                bc->idle_bytes += sz;
+                while (bc->idle_bytes > kCacheTotal && !bc->idle.empty()) {       // drop the oldest
+                    RSVD_CUDA(cudaFreeAsync(bc->idle.front().first, c.stream));
+                    bc->idle_bytes -= bc->idle.front().second;
+                    bc->idle.erase(bc->idle.begin());
+                }
+                return;
+            }
+        }
+    }
+    RSVD_CUDA(cudaFreeAsync(p, c.stream));
 }
+void release_cached_blocks() { if (ctx().inited) cache_flush(ctx()); }
 
 // ---- host <-> device -------------------------------------------------------------------------------
 static bool host_is_pinned(const void *p) {
@@ -232,6 +319,7 @@ void rsvd_b200_set_option(const char *name, rsvd_i64 value) {
     else if (!strcmp(name, "jacobi_transpose")) ctx().jacobi_transpose = (int)value;
     else if (!strcmp(name, "no_chol_dataflow")) ctx().no_chol_dataflow = (int)value;
     else if (!strcmp(name, "no_live_replay")) ctx().no_live_replay = (int)value;
+    else if (!strcmp(name, "no_block_cache")) { ctx().no_block_cache = (int)value; if (value) release_cached_blocks(); }
     else if (!strcmp(name, "force_unblocked_qr")) ctx().force_unblocked_qr = (int)value;
     else if (!strcmp(name, "no_sketch_cluster")) ctx().no_sketch_cluster = (int)value;
     else if (!strcmp(name, "qr_blocked_rows")) ctx().qr_blocked_rows = (int)value;

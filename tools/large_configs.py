@@ -78,7 +78,7 @@ if what == "c3":
     B = torch.zeros((n, cap), dtype=torch.float64, device="cuda")
     fr = C.c_longlong(0)
     print("C3: randQB_pb_new tolerance mode on %d x %d (%.1f GB), kstep=%d q=%d, ||A||_F=%.4f, TOL=%.1e (absolute)" % (m, n, 8e-9 * m * n, kstep, q, normA, tol), flush=True)
-    lib.rsvd_b200_set_option(b"verbose", 1)
+    lib.rsvd_b200_set_option(b"verbose", int(os.environ.get("RSVD_B200_VERBOSE", "1")))     # 3: per-phase CUDA-event times of every block step
     sync()
     t0 = time.time()
     native.check(lib.rsvd_b200_randqb_dev(A.data_ptr(), m, n, m, kstep, 0, tol, q, s, 777, Q.data_ptr(), m, B.data_ptr(), cap, C.byref(fr)))
