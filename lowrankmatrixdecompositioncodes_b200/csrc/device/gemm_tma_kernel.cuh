@@ -341,6 +341,20 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        // C <- C - A B on a full interior tile (the rank-kstep update of the blocked QB, RRA:1750: ~13 k-iterations per tile): the
+        // accumulators start from -C, loaded while the TMA pipeline fills, so the old values cost no latency at all and the
+        // epilogue only stores.  (-1) * (-C + sum) = C - sum exactly; only the summation order differs from alpha*acc + beta*C.
+        const bool preload = !PHILOX && !A_KMAJOR && nsplit == 1 && p.beta == 1.0 && p.alpha == -1.0 && p.c_vec2 && m0 + BM <= p.m &&
+                             n0 + 8 * NB <= p.n;
+        if (preload) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const double2 o = __ldcs(reinterpret_cast<const double2 *>(p.C + (n0 + nb * 8 + t + 4 * cc) * p.ldc + m0 + cw * 16 + 2 * g));
+                    acc[0][nb][cc] = -o.x; acc[1][nb][cc] = -o.y;
+                }
+        }
 
         // loop-invariant byte offsets inside a stage (s' = 0; s' = 1 adds 64 bytes before the XOR -> recomputed below)
         const uint32_t b_row = (uint32_t)(pg * 128);
@@ -421,7 +435,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         }
                     }
         } else {
-            const double alpha = p.alpha, beta = p.beta;
+            const double alpha = p.alpha, beta = preload ? 0.0 : p.beta;
             double ss = 0.0;          // fused Frobenius norm of the updated C (randQB_pb_new: ||A - Qp Bp||_F, RRA:1750-1751,1771)
             if (!A_KMAJOR && beta != 0.0 && p.c_vec2 && m0 + BM <= p.m && n0 + 8 * NB <= p.n) {
                 // Read-modify-write of a full interior tile (the rank-kstep update A -= Qp Bp, RRA:1750, has only ~13 k-iterations
