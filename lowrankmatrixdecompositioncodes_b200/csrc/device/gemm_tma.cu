@@ -206,7 +206,8 @@ bool gemm_tma_try(const Gemm &g) {
     if (!launched) return false;
     const i64 split_tiles = (p.s_main > 1 ? p.main_tiles : 0) + (p.s_tail > 1 ? tail_tiles : 0);
     if (split_tiles > 0) {
-        tile_reduce_kernel<<<(unsigned)(p.cl ? 2 * split_tiles : split_tiles), 256, 0, ctx().stream>>>(p, 0);
+        const unsigned rt = (unsigned)(p.cl ? 2 * split_tiles : split_tiles);
+        tile_reduce_kernel<<<dim3(rt, rt >= 64 ? 2 : 8), 256, 0, ctx().stream>>>(p, 0);
         count_launch();
     }
     if (g.sumsq_out) sum_array_async(ss_part.p, units * 8, g.sumsq_out);

@@ -528,7 +528,8 @@ static __global__ void __launch_bounds__(256) tile_reduce_kernel(TmaP p, int fir
     const int ncols = (int)min((i64)(8 * p.nb_tile), p.n - n0);
     const i64 pstride = p.cl ? 2 * (i64)PART_TILE : (i64)PART_TILE;
     const double *P = p.part + (p.cl ? ((i64)unit0 * 2 + member) : (i64)unit0) * PART_TILE;
-    for (int e = threadIdx.x; e < ncols * BM; e += blockDim.x) {
+    // gridDim.y CTAs share one tile (a Gram matrix has 10-25 tiles: one CTA each would leave the reduction to a handful of SMs)
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < ncols * BM; e += blockDim.x * gridDim.y) {
         const int r = e % BM, c = e / BM;
         const i64 row = m0 + r, col = n0 + c;
         if (row >= p.m) continue;

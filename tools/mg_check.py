@@ -93,6 +93,8 @@ def main():
 
     # ---- N devices against ONE device at a size where the partition matters, and the residency cache --------------------
     m, n, k, p, q, s = (50000, 100000, 1000, 20, 3, 1) if big else (40000, 12000, 300, 20, 2, 1)    # --big: the shape of driver1.c (64-bit ABI)
+    if "--c2" in sys.argv:      # BASELINE configs[1] from ONE host matrix: end-to-end strong scaling through the unchanged C API
+        m, n, k, p, q, s = 50000, 20000, 500, 20, 2, 1
     apiL = pkg.Api(64) if big else api
     M = apiL.lib.matrix_new(m, n)
     t0 = time.time()
