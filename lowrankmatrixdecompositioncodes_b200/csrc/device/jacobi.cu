@@ -206,10 +206,21 @@ __device__ __forceinline__ void block_sumK(double (&v)[K], double *sh) {   // sh
 // (unsigned long long *)(ctl + 4)[0] = bit pattern of the largest |cosine| met in the current sweep (positive doubles order like integers)
 // The rotations are only LOGGED (rotlog[step][slot] = (c, s), identity when nothing was rotated): V is rebuilt afterwards by
 // jacobi_replay_kernel, off the critical path.  NT threads per CTA, RPT rows per thread (NT*RPT >= n).
-template <int BW, int RPT, int NT>
+// GRAM = true: one block-wide reduction per round instead of one per step.  The CTA forms the full Gram matrix of its 2*BW columns
+// (norms and all cross products) once, right after loading them; every rotation of the round takes a, b, c from that matrix and
+// updates it algebraically (G <- J^T G J: two rows of 2x2 rotations, a - t c and b + t c on the diagonal, 0 at (p, q)), so the BW
+// (+ BW - 1 in round 0) steps of a round need no further communication between the threads: each thread just rotates its rows.
+// The matrix is rebuilt from the columns every round, so rounding errors of the algebraic updates live for one round only, and
+// they scale with the norms of the columns involved (graded accuracy is kept).  This is what makes 8 columns per CTA (BW = 4)
+// worth trying with 8 columns per CTA (BW = 4: four steps per device-wide barrier) — measured, it does not pay there: every thread
+// repeats the scalar Gram updates and rotation parameters (16 rotations x ~80 FP64 instructions per round at 16 lanes/clk per SM
+// sub-partition), 10.3 us per round against 2 x 3.8 us for two BW = 2 rounds.  With 4 columns per CTA it saves two of the three
+// reductions of a round: 3 % of the kernel time.
+template <int BW, int RPT, int NT, bool GRAM = false>
 __global__ void __launch_bounds__(NT) jacobi_persistent_kernel(double *G, i64 ldg, int n, int NBk, double tol, int max_sweeps, int *ctl,
                                                                double2 *rotlog) {
-    __shared__ double sh[2][2 * BW * (NT / 32)];
+    constexpr int NGRAM = BW * (2 * BW + 1);              // unique entries of the (2 BW) x (2 BW) Gram matrix
+    __shared__ double sh[2][(GRAM ? NGRAM : 2 * BW) * (NT / 32)];
     const int N = NBk * BW, half = N / 2;
     int gen = 0, shb = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); reinterpret_cast<unsigned long long *>(ctl)[36] = t; }
@@ -241,12 +252,72 @@ __global__ void __launch_bounds__(NT) jacobi_persistent_kernel(double *G, i64 ld
                 }
                 nrm[cc] = a;
             }
-            block_sumK<2 * BW, NT>(nrm, sh[shb]); shb ^= 1;
             bool dirty[2 * BW];
 #pragma unroll
             for (int cc = 0; cc < 2 * BW; ++cc) dirty[cc] = false;
-            // ---- the steps of this round: intra-block pairs first (round 0 only), then the BW cross steps
             const int nintra = (BW > 1 && rb == 0) ? BW - 1 : 0;
+            if constexpr (GRAM) {
+                // ---- Gram matrix of the 2*BW columns: gm[gidx(p, q)], p <= q
+                auto gidx = [](int p_, int q_) { return p_ * (2 * BW) - p_ * (p_ - 1) / 2 + (q_ - p_); };
+                double gm[NGRAM];
+#pragma unroll
+                for (int p_ = 0; p_ < 2 * BW; ++p_) {
+                    gm[gidx(p_, p_)] = nrm[p_];
+#pragma unroll
+                    for (int q_ = p_ + 1; q_ < 2 * BW; ++q_) {
+                        double c = 0.0;
+#pragma unroll
+                        for (int k = 0; k < RPT; ++k) c = fma(X[p_][k], X[q_][k], c);
+                        gm[gidx(p_, q_)] = c;
+                    }
+                }
+                block_sumK<NGRAM, NT>(gm, sh[shb]); shb ^= 1;
+#pragma unroll
+                for (int stp = 0; stp < (BW > 1 ? BW - 1 : 0) + BW; ++stp) {
+                    const bool intra = stp < (BW > 1 ? BW - 1 : 0);
+                    if (intra && nintra == 0) continue;
+#pragma unroll
+                    for (int j = 0; j < BW; ++j) {
+                        int pa, pb;
+                        if (intra) intra_pair<(BW > 1 ? BW : 2)>(stp, j, pa, pb);
+                        else { pa = j; pb = BW + (j + (stp - (BW > 1 ? BW - 1 : 0))) % BW; }
+                        const int lo = pa < pb ? pa : pb, hi = pa < pb ? pb : pa;
+                        const double a = gm[gidx(pa, pa)], b = gm[gidx(pb, pb)], c = gm[gidx(lo, hi)];
+                        double2 applied = make_double2(1.0, 0.0);
+                        const double ab = a * b;
+                        const bool inrange = ab > 1e-280 && ab < 1e280;
+                        if ((inrange ? c * c > tol * tol * ab : fabs(c) > tol * sqrt(a) * sqrt(b)) && a != 0.0 && b != 0.0) {
+                            double cs, sn, t;
+                            rot_params(a, b, c, cs, sn, t);
+                            rotated = 1;
+                            cmax = fmax(cmax, inrange ? c * c * rcp_seed(ab) : (c / a) * (c / b));
+#pragma unroll
+                            for (int k = 0; k < RPT; ++k) {
+                                const double x = X[pa][k], y = X[pb][k];
+                                X[pa][k] = cs * x - sn * y;
+                                X[pb][k] = sn * x + cs * y;
+                            }
+#pragma unroll
+                            for (int r_ = 0; r_ < 2 * BW; ++r_) {
+                                if (r_ == pa || r_ == pb) continue;
+                                const int ia = r_ < pa ? gidx(r_, pa) : gidx(pa, r_), ib = r_ < pb ? gidx(r_, pb) : gidx(pb, r_);
+                                const double ga = gm[ia], gb = gm[ib];
+                                gm[ia] = cs * ga - sn * gb;
+                                gm[ib] = sn * ga + cs * gb;
+                            }
+                            gm[gidx(pa, pa)] = fmax(a - t * c, 0.0);
+                            gm[gidx(pb, pb)] = b + t * c;
+                            gm[gidx(lo, hi)] = 0.0;
+                            dirty[pa] = true; dirty[pb] = true;
+                            applied = make_double2(cs, sn);
+                        }
+                        if (threadIdx.x == 0) rotlog[gs * half + i * BW + j] = applied;
+                    }
+                    ++gs;
+                }
+            } else {
+            block_sumK<2 * BW, NT>(nrm, sh[shb]); shb ^= 1;
+            // ---- the steps of this round: intra-block pairs first (round 0 only), then the BW cross steps
 #pragma unroll
             for (int stp = 0; stp < (BW > 1 ? BW - 1 : 0) + BW; ++stp) {
                 const bool intra = stp < (BW > 1 ? BW - 1 : 0);
@@ -288,6 +359,7 @@ __global__ void __launch_bounds__(NT) jacobi_persistent_kernel(double *G, i64 ld
                     if (threadIdx.x == 0) rotlog[gs * half + i * BW + j] = applied;
                 }
                 ++gs;
+            }
             }
             // ---- write the rotated columns back
 #pragma unroll
@@ -487,11 +559,11 @@ static void launch_replay_live(double *V, i64 ldv, int n, int NBk, const double2
 }
 
 // one (BW, RPT) instantiation of the persistent path; returns sweeps, -1 on a barrier time-out, -2 when it could not launch
-template <int BW, int RPT, int NT = JT>
+template <int BW, int RPT, int NT = JT, bool GRAM = false>
 static int run_persistent(double *G, i64 ldg, double *V, i64 ldv, int n, double tol, int max_sweeps) {
     Ctx &c = ctx();
     static int blocks_per_sm = -1;
-    if (blocks_per_sm < 0) RSVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_persistent_kernel<BW, RPT, NT>, NT, 0));
+    if (blocks_per_sm < 0) RSVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_persistent_kernel<BW, RPT, NT, GRAM>, NT, 0));
     int NBk = 2 * ((n + 2 * BW - 1) / (2 * BW));
     const int N = NBk * BW, half = N / 2;
     if (half > 1024 || blocks_per_sm < 1) return -2;
@@ -514,11 +586,11 @@ static int run_persistent(double *G, i64 ldg, double *V, i64 ldv, int n, double 
     // the replay CTAs fit beside it) and the barrier's bounded spin turns a grid that is not co-resident into an error.
     cudaError_t e;
     if (live) {
-        RSVD_CUDA(cudaFuncSetAttribute(jacobi_persistent_kernel<BW, RPT, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        jacobi_persistent_kernel<BW, RPT, NT><<<grid, NT, 0, c.stream>>>(G, ldg, n, NBk, tol, ms, ctl, rotlog);
+        RSVD_CUDA(cudaFuncSetAttribute(jacobi_persistent_kernel<BW, RPT, NT, GRAM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        jacobi_persistent_kernel<BW, RPT, NT, GRAM><<<grid, NT, 0, c.stream>>>(G, ldg, n, NBk, tol, ms, ctl, rotlog);
         e = cudaGetLastError();
     } else {
-        e = cudaLaunchCooperativeKernel((void *)jacobi_persistent_kernel<BW, RPT, NT>, dim3(grid), dim3(NT), args, 0, c.stream);
+        e = cudaLaunchCooperativeKernel((void *)jacobi_persistent_kernel<BW, RPT, NT, GRAM>, dim3(grid), dim3(NT), args, 0, c.stream);
     }
     int sweeps = -2;
     if (e == cudaSuccess) {
@@ -548,8 +620,8 @@ static int run_persistent(double *G, i64 ldg, double *V, i64 ldv, int n, double 
                 else launch_replay<8, BW>(V, ldv, n, NBk, steps, rotlog, c.stream);
                 count_launch();
             }
-            if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d (persistent, %d columns per CTA%s)\n", n, sweeps, 2 * BW,
-                                   live ? (c.h_flag[20] ? ", live replay gave up" : ", live replay") : "");
+            if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d (persistent, %d columns per CTA%s%s)\n", n, sweeps, 2 * BW,
+                                   GRAM ? ", one Gram reduction per round" : "", live ? (c.h_flag[20] ? ", live replay gave up" : ", live replay") : "");
         }
     } else {
         (void)cudaGetLastError();
@@ -603,7 +675,11 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
         static int bw = -1;
         if (bw < 0) { const char *e = getenv("RSVD_B200_JACOBI_BW"); bw = e ? atoi(e) : 2; }
         int r;
-        if (n <= JT * 5) r = (bw == 4) ? run_persistent<4, 5>(G, ldg, V, ldv, n, tol, max_sweeps)
+        static int gram = -1;
+        if (gram < 0) { const char *e = getenv("RSVD_B200_JACOBI_GRAM"); gram = e ? atoi(e) : 2; }   // measured at n = 520, 20 sweeps: 4 columns/CTA 20.06 ms, + Gram 19.43, 8 columns + Gram 27.1
+        if (n <= JT * 5 && gram == 4) r = run_persistent<4, 5, JT, true>(G, ldg, V, ldv, n, tol, max_sweeps);
+        else if (n <= JT * 5 && gram == 2) r = run_persistent<2, 5, JT, true>(G, ldg, V, ldv, n, tol, max_sweeps);
+        else if (n <= JT * 5) r = (bw == 4) ? run_persistent<4, 5>(G, ldg, V, ldv, n, tol, max_sweeps)
                            : (bw == 1) ? run_persistent<1, 5>(G, ldg, V, ldv, n, tol, max_sweeps)
                                        : run_persistent<2, 5>(G, ldg, V, ldv, n, tol, max_sweeps);
         else if (n <= JT * 10) r = (bw == 1) ? run_persistent<1, 10>(G, ldg, V, ldv, n, tol, max_sweeps)
