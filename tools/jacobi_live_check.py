@@ -7,7 +7,7 @@ from lowrankmatrixdecompositioncodes_b200 import native, device as D
 lib = native.dev()
 assert lib.rsvd_b200_init(0) == 0
 ok_all = True
-for n in ((64, 130, 520, 592) if os.environ.get("RSVD_B200_JACOBI_GRAM") else (2, 7, 64, 130, 520, 592, 593, 777, 1050)):
+for n in ((130, 520) if os.environ.get("RSVD_B200_JACOBI_GRAM") else (2, 7, 64, 130, 520, 592, 593, 777, 1050)):
     rng = np.random.default_rng(n)
     U0, _ = np.linalg.qr(rng.standard_normal((n, n)))
     V0, _ = np.linalg.qr(rng.standard_normal((n, n)))
