@@ -204,19 +204,22 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 def gen_lowrank(torch, m, n, r, lo, noise, seed, rank, m_global):
     """This rank's m rows of A = X diag(logspace(1, lo, r)) W^T + noise, column-major (tensor of shape (n, m)), built in
-    HBM in column slabs.  torch only generates data, outside every timed region."""
+    HBM in column slabs.  torch only draws the random factors, outside every timed region."""
     g = torch.Generator(device="cuda").manual_seed(seed + 1000 * rank)
     gw = torch.Generator(device="cuda").manual_seed(seed + 7)               # the same W on every rank
     X = torch.randn((m, r), dtype=torch.float64, device="cuda", generator=g) / (m_global ** 0.5)
     W = torch.randn((n, r), dtype=torch.float64, device="cuda", generator=gw) / (n ** 0.5)
     sig = torch.logspace(1, lo, r, dtype=torch.float64, device="cuda")
     A = torch.empty((n, m), dtype=torch.float64, device="cuda")
+    from lowrankmatrixdecompositioncodes_b200 import device as D
+    Xcm = X.t().contiguous()                     # column-major m x r
+    Ws = (W * sig).contiguous()                  # (n, r) row-major = column-major r x n: the K-major operand of the library's own GEMM
     step = 1024
     for j0 in range(0, n, step):
         j1 = min(n, j0 + step)
-        torch.matmul(W[j0:j1] * sig, X.t(), out=A[j0:j1])
+        D.gemm("N", "N", m, j1 - j0, r, Xcm, m, Ws[j0:j1], r, A[j0:j1], m)      # A(:, j0:j1) = X diag(sig) W(j0:j1, :)^T — no cuBLAS anywhere in the run
         A[j0:j1].add_(torch.randn((j1 - j0, m), dtype=torch.float64, device="cuda", generator=g), alpha=noise)
-    del X, W
+    del X, W, Xcm, Ws
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     return A, sig
@@ -379,7 +382,7 @@ def main():
     st = D.stream()
 
     # synthetic input generated in HBM (rank-r core with the reference generator's logspace(1,-3) spectrum + noise floor);
-    # each rank builds only its own rows.  torch (cuBLAS) is used for data generation only, outside every timed region.
+    # each rank builds only its own rows.  torch draws the random factors; the product is the library's own GEMM (no cuBLAS in the run).
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
     r = 640
     X = torch.randn((m, r), dtype=torch.float64, device="cuda", generator=g) / (m_global ** 0.5)
@@ -387,11 +390,13 @@ def main():
     W = torch.randn((n, r), dtype=torch.float64, device="cuda", generator=gw) / (n ** 0.5)
     sig = torch.logspace(1, -3, r, dtype=torch.float64, device="cuda")
     A_cm = torch.empty((n, m), dtype=torch.float64, device="cuda")          # column-major m x n
+    Xcm = X.t().contiguous()                     # column-major m x r
+    Ws = (W * sig).contiguous()                  # (n, r) row-major = column-major r x n: the K-major operand of the library's own GEMM
     for j0 in range(0, n, 4096):
         j1 = min(n, j0 + 4096)
-        torch.matmul(W[j0:j1] * sig, X.t(), out=A_cm[j0:j1])
+        D.gemm("N", "N", m, j1 - j0, r, Xcm, m, Ws[j0:j1], r, A_cm[j0:j1], m)   # A(:, j0:j1) = X diag(sig) W(j0:j1, :)^T
         A_cm[j0:j1] += 1e-6 * torch.randn((j1 - j0, m), dtype=torch.float64, device="cuda", generator=g)
-    del X, W
+    del X, W, Xcm, Ws
     U = D.new_cm(m, K); V = D.new_cm(n, K)
     Sv = torch.empty(K, dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
