@@ -36,7 +36,7 @@ void rsvd_b200_sync(void);
 unsigned long long rsvd_b200_launch_count(void); /* kernels launched by this library so far */
 /* options: "seed" (Omega seed, default 777 = the reference's unused `#define SEED 777`, MVH:10),
  * "verbose" (1 messages, 2 synchronising phase timer, 3 CUDA-event phase times), "force_generic_gemm",
- * "force_qr_fallback" (1: TSQR-preconditioned path for every panel), "force_unblocked_qr", "single_device" (host-level calls
+ * "force_qr_fallback" (1: TSQR-preconditioned path for every panel, 2: shifted CholeskyQR3), "force_unblocked_qr", "single_device" (host-level calls
  * ignore the worker pool); A/B switches of individual kernels, all default 0: "no_sketch_cluster", "no_chol_dataflow" (l x l
  * Cholesky + inverse as a per-block launch sequence), "no_live_replay" (Jacobi's V rebuilt after the rotations instead of next
  * to them), "no_block_cache" (freed work buffers go straight back to the CUDA memory pool), "jacobi_transpose";

@@ -108,7 +108,8 @@ def test_gemm_linearity_at_scale(lib):
 
 
 @pytest.mark.parametrize("m,l,cond,force", [(5000, 120, 1e3, 0), (5000, 120, 1e12, 0), (3000, 200, 1e2, 1), (20000, 520, 1e5, 0),
-                                            (64, 64, 10, 0), (1000, 1, 1, 0), (5000, 120, 1e12, 1), (30000, 200, 1e9, 0), (4000, 300, 1e14, 0)])
+                                            (64, 64, 10, 0), (1000, 1, 1, 0), (5000, 120, 1e12, 1), (30000, 200, 1e9, 0), (4000, 300, 1e14, 0),
+                                            (3000, 200, 1e2, 2)])
 def test_orthonormalize(lib, m, l, cond, force):
     rng = np.random.default_rng(3)
     Q0, _ = np.linalg.qr(rng.standard_normal((m, l)))
@@ -121,8 +122,8 @@ def test_orthonormalize(lib, m, l, cond, force):
     sync(lib)
     lib.rsvd_b200_set_option(b"force_qr_fallback", 0)
     path = lib.rsvd_b200_get_option(b"last_qr_path")
-    # 1 = CholeskyQR2, 4 = shifted CholeskyQR3 (cond beyond the plain pass's limit), 2 = TSQR-preconditioned (forced here)
-    assert path == (2 if force else 4 if cond > 1e8 else 1)
+    # 1 = CholeskyQR2, 4 = shifted CholeskyQR3 (cond beyond the plain pass's limit, or forced with 2), 2 = TSQR-preconditioned (forced with 1)
+    assert path == (2 if force == 1 else 4 if (force == 2 or cond > 1e8) else 1)
     Q, Rn = D.to_numpy(Yd), R.t().cpu().numpy()
     assert np.abs(Q.T @ Q - np.eye(l)).max() < 1e-13
     assert np.linalg.norm(Q @ Rn - Y) / np.linalg.norm(Y) < 1e-13
