@@ -215,11 +215,11 @@ __device__ __forceinline__ void block_sumK(double (&v)[K], double *sh) {   // sh
 // updates it algebraically (G <- J^T G J: two rows of 2x2 rotations, a - t c and b + t c on the diagonal, 0 at (p, q)), so the BW
 // (+ BW - 1 in round 0) steps of a round need no further communication between the threads: each thread just rotates its rows.
 // The matrix is rebuilt from the columns every round, so rounding errors of the algebraic updates live for one round only, and
-// they scale with the norms of the columns involved (graded accuracy is kept).  This is what makes 8 columns per CTA (BW = 4)
-// worth trying with 8 columns per CTA (BW = 4: four steps per device-wide barrier) — measured, it does not pay there: every thread
-// repeats the scalar Gram updates and rotation parameters (16 rotations x ~80 FP64 instructions per round at 16 lanes/clk per SM
-// sub-partition), 10.3 us per round against 2 x 3.8 us for two BW = 2 rounds.  With 4 columns per CTA it saves two of the three
-// reductions of a round: 3 % of the kernel time.
+// they scale with the norms of the columns involved (graded accuracy is kept).  With 4 columns per CTA (BW = 2) this saves two of
+// the three reductions of a round: 3 % of the kernel time.  It was also the reason to try 8 columns per CTA (BW = 4: four steps
+// per device-wide barrier) — measured, that does not pay: every thread repeats the scalar Gram updates and rotation parameters
+// (16 rotations x ~80 FP64 instructions per round at 16 lanes/clk per SM sub-partition), 10.3 us per round against 2 x 3.8 us
+// for two BW = 2 rounds.
 template <int BW, int RPT, int NT, bool GRAM = false>
 __global__ void __launch_bounds__(NT) jacobi_persistent_kernel(double *G, i64 ldg, int n, int NBk, double tol, int max_sweeps, int *ctl,
                                                                double2 *rotlog) {
