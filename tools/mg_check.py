@@ -63,33 +63,34 @@ def main():
     api = pkg.Api(32)
     L = ref_lib.RefLib(32) if ref_lib.available(32) else None
 
-    # ---- against the compiled reference, same Omega -------------------------------------------------------------------
-    for (m, n, k, p, q, s, spec) in [(6000, 1500, 100, 20, 2, 1, "gap"), (9001, 900, 40, 10, 2, 1, "logspace")]:
-        A, _ = O.make_matrix(m, n, spec, seed=3, k=k, tail=1e-7)
-        U, S, V = api.svd_rand(A, k, p, 1, q, s, seed=777)
-        Ur, Sr, Vr = quiet(lambda: L.svd_rand(A, k, p, 1, q, s, seed=777)) if L else O.low_rank_svd_rand_decomp_fixed_rank(A, k, p, 1, q, s, 777)
-        rel = float(np.max(np.abs(np.diag(S) - np.diag(Sr)) / np.diag(Sr)))
-        e, er = np.linalg.norm(A - U @ S @ V.T) / np.linalg.norm(A), np.linalg.norm(A - Ur @ Sr @ Vr.T) / np.linalg.norm(A)
-        report("svd_rand %dx%d on %d GPUs (%s)" % (m, n, want, spec), rel < 1e-10 and abs(e - er) <= 0.01 * er and sin_theta(U, Ur) < 1e-6,
-               "max rel sigma err %.2e  sin(theta) U %.2e  recon %.6e (ref %.6e)  ||UtU-I|| %.1e" % (rel, sin_theta(U, Ur), e, er, np.abs(U.T @ U - np.eye(k)).max()))
-        Ic, Ir, T, Sm = api.id_two_sided_rand(A, k, p, q, s, seed=777)
-        Icr, Irr, Tr, Smr = quiet(lambda: L.id_two_sided_rand(A, k, p, q, s, seed=777)) if L else O.id_two_sided_rand_decomp_fixed_rank(A, k, p, q, s, 777)
-        report("id_two_sided %dx%d on %d GPUs" % (m, n, want), np.array_equal(Ic, Icr) and np.array_equal(Ir, Irr) and np.abs(T - Tr).max() < 1e-9 and np.abs(Sm - Smr).max() < 1e-9,
-               "Icol bit-exact %s  Irow bit-exact %s  max|T-Tref| %.2e  max|S-Sref| %.2e" % (np.array_equal(Ic, Icr), np.array_equal(Ir, Irr), np.abs(T - Tr).max(), np.abs(Sm - Smr).max()))
-        Cm, Um, Rm = api.cur_rand(A, k, p, q, s, seed=777)
-        Cr, Uc, Rr = quiet(lambda: L.cur_rand(A, k, p, q, s, seed=777)) if L else O.cur_rand_decomp_fixed_rank(A, k, p, q, s, 777)
-        report("cur_rand %dx%d on %d GPUs" % (m, n, want), np.array_equal(Cm, Cr) and np.array_equal(Rm, Rr) and np.abs(Um - Uc).max() <= 1e-6 * np.abs(Uc).max(),
-               "C bit-exact %s  R bit-exact %s  max|U-Uref|/max|U| %.2e" % (np.array_equal(Cm, Cr), np.array_equal(Rm, Rr), np.abs(Um - Uc).max() / np.abs(Uc).max()))
-        for (kstep, nstep, tol) in [(20, 4, 0.0), (20, 0, float(np.linalg.norm(A)) * 0.3)]:
-            f, Qm, Bm = api.randQB_pb_new(A, kstep, nstep, tol, q, s, seed=777)
-            fr, Qr, Br = quiet(lambda: L.randQB_pb_new(A, kstep, nstep, tol, q, s, seed=777)) if L else O.randQB_pb_new(A, kstep, nstep, tol, q, s, 777)
-            d = np.linalg.norm(Qm @ Bm - Qr @ Br) / np.linalg.norm(A)
-            report("randQB_pb_new kstep=%d nstep=%d tol=%.3g on %d GPUs" % (kstep, nstep, tol, want), f == fr and d < 1e-11, "frank %d (ref %d)  ||QB-QrBr||/||A|| %.2e" % (f, fr, d))
-        fo, U, S, V = api.svd_blockrand(A, 60, 20, 0.0, 1, 20, q, s, seed=777)
-        frr, Ur, Sr, Vr = quiet(lambda: L.svd_blockrand(A, 60, 20, 0.0, 1, 20, q, s, seed=777)) if L else O.low_rank_svd_blockrand_decomp_fixed_rank_or_prec(A, 60, 20, 0.0, 1, 20, q, s, 777)
-        rel = float(np.max(np.abs(np.diag(S) - np.diag(Sr)) / np.diag(Sr)))
-        report("low_rank_svd_blockrand k=60 p=20 kstep=20 on %d GPUs" % want, fo == frr and rel < 1e-10 and sin_theta(U, Ur) < 1e-6,
-               "frank %d (ref %d)  max rel sigma err %.2e  sin(theta) U %.2e" % (fo, frr, rel, sin_theta(U, Ur)))
+    if "--only-scale" not in sys.argv:
+        # ---- against the compiled reference, same Omega -------------------------------------------------------------------
+        for (m, n, k, p, q, s, spec) in [(6000, 1500, 100, 20, 2, 1, "gap"), (9001, 900, 40, 10, 2, 1, "logspace")]:
+            A, _ = O.make_matrix(m, n, spec, seed=3, k=k, tail=1e-7)
+            U, S, V = api.svd_rand(A, k, p, 1, q, s, seed=777)
+            Ur, Sr, Vr = quiet(lambda: L.svd_rand(A, k, p, 1, q, s, seed=777)) if L else O.low_rank_svd_rand_decomp_fixed_rank(A, k, p, 1, q, s, 777)
+            rel = float(np.max(np.abs(np.diag(S) - np.diag(Sr)) / np.diag(Sr)))
+            e, er = np.linalg.norm(A - U @ S @ V.T) / np.linalg.norm(A), np.linalg.norm(A - Ur @ Sr @ Vr.T) / np.linalg.norm(A)
+            report("svd_rand %dx%d on %d GPUs (%s)" % (m, n, want, spec), rel < 1e-10 and abs(e - er) <= 0.01 * er and sin_theta(U, Ur) < 1e-6,
+                   "max rel sigma err %.2e  sin(theta) U %.2e  recon %.6e (ref %.6e)  ||UtU-I|| %.1e" % (rel, sin_theta(U, Ur), e, er, np.abs(U.T @ U - np.eye(k)).max()))
+            Ic, Ir, T, Sm = api.id_two_sided_rand(A, k, p, q, s, seed=777)
+            Icr, Irr, Tr, Smr = quiet(lambda: L.id_two_sided_rand(A, k, p, q, s, seed=777)) if L else O.id_two_sided_rand_decomp_fixed_rank(A, k, p, q, s, 777)
+            report("id_two_sided %dx%d on %d GPUs" % (m, n, want), np.array_equal(Ic, Icr) and np.array_equal(Ir, Irr) and np.abs(T - Tr).max() < 1e-9 and np.abs(Sm - Smr).max() < 1e-9,
+                   "Icol bit-exact %s  Irow bit-exact %s  max|T-Tref| %.2e  max|S-Sref| %.2e" % (np.array_equal(Ic, Icr), np.array_equal(Ir, Irr), np.abs(T - Tr).max(), np.abs(Sm - Smr).max()))
+            Cm, Um, Rm = api.cur_rand(A, k, p, q, s, seed=777)
+            Cr, Uc, Rr = quiet(lambda: L.cur_rand(A, k, p, q, s, seed=777)) if L else O.cur_rand_decomp_fixed_rank(A, k, p, q, s, 777)
+            report("cur_rand %dx%d on %d GPUs" % (m, n, want), np.array_equal(Cm, Cr) and np.array_equal(Rm, Rr) and np.abs(Um - Uc).max() <= 1e-6 * np.abs(Uc).max(),
+                   "C bit-exact %s  R bit-exact %s  max|U-Uref|/max|U| %.2e" % (np.array_equal(Cm, Cr), np.array_equal(Rm, Rr), np.abs(Um - Uc).max() / np.abs(Uc).max()))
+            for (kstep, nstep, tol) in [(20, 4, 0.0), (20, 0, float(np.linalg.norm(A)) * 0.3)]:
+                f, Qm, Bm = api.randQB_pb_new(A, kstep, nstep, tol, q, s, seed=777)
+                fr, Qr, Br = quiet(lambda: L.randQB_pb_new(A, kstep, nstep, tol, q, s, seed=777)) if L else O.randQB_pb_new(A, kstep, nstep, tol, q, s, 777)
+                d = np.linalg.norm(Qm @ Bm - Qr @ Br) / np.linalg.norm(A)
+                report("randQB_pb_new kstep=%d nstep=%d tol=%.3g on %d GPUs" % (kstep, nstep, tol, want), f == fr and d < 1e-11, "frank %d (ref %d)  ||QB-QrBr||/||A|| %.2e" % (f, fr, d))
+            fo, U, S, V = api.svd_blockrand(A, 60, 20, 0.0, 1, 20, q, s, seed=777)
+            frr, Ur, Sr, Vr = quiet(lambda: L.svd_blockrand(A, 60, 20, 0.0, 1, 20, q, s, seed=777)) if L else O.low_rank_svd_blockrand_decomp_fixed_rank_or_prec(A, 60, 20, 0.0, 1, 20, q, s, 777)
+            rel = float(np.max(np.abs(np.diag(S) - np.diag(Sr)) / np.diag(Sr)))
+            report("low_rank_svd_blockrand k=60 p=20 kstep=20 on %d GPUs" % want, fo == frr and rel < 1e-10 and sin_theta(U, Ur) < 1e-6,
+                   "frank %d (ref %d)  max rel sigma err %.2e  sin(theta) U %.2e" % (fo, frr, rel, sin_theta(U, Ur)))
 
     # ---- N devices against ONE device at a size where the partition matters, and the residency cache --------------------
     m, n, k, p, q, s = (50000, 100000, 1000, 20, 3, 1) if big else (40000, 12000, 300, 20, 2, 1)    # --big: the shape of driver1.c (64-bit ABI)
