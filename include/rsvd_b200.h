@@ -153,7 +153,7 @@ int rsvd_b200_randqb_single_dev(double *Awork, rsvd_i64 m, rsvd_i64 n, rsvd_i64 
 /* SVD factors from (Q, B) in ASCENDING singular-value order: tail of randomized_low_rank_svd4 (RRA:660-688, dsyev order). */
 int rsvd_b200_svd_from_qb_asc_dev(const double *Q, rsvd_i64 m, rsvd_i64 ldq, const double *B, rsvd_i64 l, rsvd_i64 n, rsvd_i64 ldb, double *U,
                                   rsvd_i64 ldu, double *S, double *V, rsvd_i64 ldv);
-/* full thin SVD A = U diag(S) V^T, r = min(m,n) (dgesvd 'S','S' of low_rank_svd_decomp_fixed_rank_or_prec, RRA:7-69); r <= 2048 (Jacobi kernel limit). */
+/* full thin SVD A = U diag(S) V^T, r = min(m,n) (dgesvd 'S','S' of low_rank_svd_decomp_fixed_rank_or_prec, RRA:7-69); r <= 4096 (Jacobi kernel limit). */
 int rsvd_b200_svd_full_dev(const double *A, rsvd_i64 m, rsvd_i64 n, rsvd_i64 lda, double *U, rsvd_i64 ldu, double *S, double *V,
                            rsvd_i64 ldv);
 /* estimate_rank_and_buildQ (MVF:1339-1400): sketch of width maxdim, sequential Gram-Schmidt with the reference's stop rule;

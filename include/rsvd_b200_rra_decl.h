@@ -4,7 +4,7 @@
  *
  * LIMITS of this build (violations are reported through rsvd_b200_api_status() / rsvd_b200_api_last_error(); outputs are still
  * allocated, zero-filled, so existing matrix_delete calls stay safe):
- *   - sketch width k + p <= 2048, and min(m, n) <= 2048 for the full-SVD baseline low_rank_svd_decomp_fixed_rank_or_prec
+ *   - sketch width k + p <= 4096, and min(m, n) <= 4096 for the full-SVD baseline low_rank_svd_decomp_fixed_rank_or_prec
  *     (the l x l factor goes through the one-sided Jacobi kernel);
  *   - k + p <= min(m, n), s > 0 (unchecked undefined behaviour in the reference);
  *   - several GPUs (RSVD_B200_DEVICES=0-7, or one process per GPU): the hot-path entry points

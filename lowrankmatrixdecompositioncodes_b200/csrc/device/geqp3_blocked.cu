@@ -496,7 +496,8 @@ void qp_factor(double *A, i64 lda, int m, int nloc, int col0, int n_global, bool
 }  // namespace
 
 // Row limit of the blocked kernel (one warp per column, the reflector in shared memory).  The default, 2048, is the widest
-// sketch the pipeline accepts (k + p <= 2048, the Jacobi kernel's limit); option "qr_blocked_rows" raises it up to 4096.
+// sketch the benchmarks use; sketches of up to 4096 rows (the Jacobi kernel's limit on k + p) go to the one-reflector-per-step kernel
+// unless option "qr_blocked_rows" raises the limit (up to 4096).
 bool geqp3_blocked_ok(i64 m, i64 n) {
     const i64 lim = std::min<i64>(4096, std::max<i64>(1, ctx().qr_blocked_rows));
     return m >= 1 && m <= lim && n >= 1 && n < (1ll << 31) - 64;

@@ -22,7 +22,7 @@ namespace {
 
 constexpr int JT = 128;     // threads per pair
 constexpr int JR = 10;      // rows per thread of the graph fallback: n <= 1280
-constexpr int JMAX = 2048;  // persistent path: 256 threads x 8 rows per column and 1024 pair slots in the replay kernel
+constexpr int JMAX = 4096;  // persistent path: 256 threads x 16 rows per column; above 2048 the replay kernel serves several pair slots per thread
 
 __device__ __forceinline__ double block_sum3(double &a, double &b, double &c, double *sh) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -544,12 +544,59 @@ __global__ void __launch_bounds__(RR == 4 ? 608 : 1024) jacobi_replay_live_kerne
     if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); reinterpret_cast<unsigned long long *>(ctl)[39] = t; }
 }
 
+// Replay for n > 2048 (more than 1024 pair slots): a thread serves the slots threadIdx.x, threadIdx.x + blockDim.x, ... of every
+// step (pairs of a step are disjoint, so the order does not matter) and reads its log entries directly — one L2 round trip per
+// step, a few percent of the Jacobi kernel's own time at these sizes.  RR rows of V per CTA in shared memory.
+template <int RR, int BW>
+__global__ void __launch_bounds__(512) jacobi_replay_wide_kernel(double *V, i64 ldv, int n, int NBk, i64 total_steps,
+                                                                 const double2 *__restrict__ rotlog) {
+    extern __shared__ __align__(16) double T[];          // [N][RR]
+    const int N = NBk * BW, half = N / 2;
+    const int r0 = blockIdx.x * RR;
+    for (int e = threadIdx.x; e < N * RR; e += blockDim.x) {
+        const int col = e / RR, rr = e % RR;
+        T[e] = (col == r0 + rr) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    int st = 0;
+    for (i64 g = 0; g < total_steps; ++g) {
+        for (int slot = threadIdx.x; slot < half; slot += blockDim.x) {
+            const double2 cs_sn = __ldg(rotlog + g * half + slot);
+            if (cs_sn.y != 0.0) {
+                int p, q;
+                pair_at<BW>(NBk, st, slot / BW, slot % BW, p, q);
+                double2 *tp = reinterpret_cast<double2 *>(T + p * RR), *tq = reinterpret_cast<double2 *>(T + q * RR);
+                const double cs = cs_sn.x, sn = cs_sn.y;
+#pragma unroll
+                for (int h = 0; h < RR / 2; ++h) {
+                    const double2 x = tp[h], y = tq[h];
+                    tp[h] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
+                    tq[h] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
+                }
+            }
+        }
+        if (++st == N - 1) st = 0;
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < n * RR; e += blockDim.x) {
+        const int col = e / RR, rr = e % RR;
+        if (r0 + rr < n) V[(i64)col * ldv + r0 + rr] = T[e];
+    }
+}
+
 template <int RR, int BW>
 static void launch_replay(double *V, i64 ldv, int n, int NBk, i64 steps, const double2 *rotlog, cudaStream_t st) {
     const int N = NBk * BW;
     const size_t smem = (size_t)N * RR * sizeof(double);
     RSVD_CUDA(cudaFuncSetAttribute(jacobi_replay_kernel<RR, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     jacobi_replay_kernel<RR, BW><<<(n + RR - 1) / RR, (N / 2 + 31) / 32 * 32, smem, st>>>(V, ldv, n, NBk, steps, rotlog);
+}
+template <int RR, int BW>
+static void launch_replay_wide(double *V, i64 ldv, int n, int NBk, i64 steps, const double2 *rotlog, cudaStream_t st) {
+    const int N = NBk * BW;
+    const size_t smem = (size_t)N * RR * sizeof(double);
+    RSVD_CUDA(cudaFuncSetAttribute(jacobi_replay_wide_kernel<RR, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jacobi_replay_wide_kernel<RR, BW><<<(n + RR - 1) / RR, 512, smem, st>>>(V, ldv, n, NBk, steps, rotlog);
 }
 template <int RR, int BW>
 static void launch_replay_live(double *V, i64 ldv, int n, int NBk, const double2 *rotlog, int *ctl, cudaStream_t st) {
@@ -570,10 +617,10 @@ static int run_persistent(double *G, i64 ldg, double *V, i64 ldv, int n, double 
     if (blocks_per_sm < 0) RSVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, jacobi_persistent_kernel<BW, RPT, NT, GRAM>, NT, 0));
     int NBk = 2 * ((n + 2 * BW - 1) / (2 * BW));
     const int N = NBk * BW, half = N / 2;
-    if (half > 1024 || blocks_per_sm < 1) return -2;
+    if (half > 2048 || blocks_per_sm < 1) return -2;
     const int grid = std::min(NBk / 2, blocks_per_sm * c.sms);
     const size_t log_entries = (size_t)max_sweeps * (N - 1) * half;
-    if (log_entries * sizeof(double2) > ((size_t)3 << 30)) return -2;
+    if (log_entries * sizeof(double2) > ((size_t)8 << 30)) return -2;
     int *ctl = (int *)dalloc_bytes(128 * sizeof(int));
     double2 *rotlog = (double2 *)dalloc_bytes(log_entries * sizeof(double2));
     if (g_status) return -2;
@@ -621,7 +668,8 @@ static int run_persistent(double *G, i64 ldg, double *V, i64 ldv, int n, double 
             const i64 steps = (i64)sweeps * (N - 1);
             if (!live || c.h_flag[20]) {      // after the fact (large n, option, or the live replay saw no progress and gave up)
                 if (n <= 1184) launch_replay<4, BW>(V, ldv, n, NBk, steps, rotlog, c.stream);   // <= 2 CTAs per SM, one wave
-                else launch_replay<8, BW>(V, ldv, n, NBk, steps, rotlog, c.stream);
+                else if (half <= 1024) launch_replay<8, BW>(V, ldv, n, NBk, steps, rotlog, c.stream);
+                else launch_replay_wide<4, BW>(V, ldv, n, NBk, steps, rotlog, c.stream);        // n > 2048: several pair slots per thread
                 count_launch();
             }
             if (c.verbose) fprintf(stderr, "[rsvd_b200] jacobi n=%d sweeps=%d (persistent, %d columns per CTA%s%s)\n", n, sweeps, 2 * BW,
@@ -688,7 +736,8 @@ int jacobi_core(double *G, i64 ldg, double *V, i64 ldv, int n) {
                                        : run_persistent<2, 5>(G, ldg, V, ldv, n, tol, max_sweeps);
         else if (n <= JT * 10) r = (bw == 1) ? run_persistent<1, 10>(G, ldg, V, ldv, n, tol, max_sweeps)
                                              : run_persistent<2, 10>(G, ldg, V, ldv, n, tol, max_sweeps);
-        else r = run_persistent<2, 8, 256>(G, ldg, V, ldv, n, tol, max_sweeps);     // 256 threads x 8 rows: 2 CTAs per SM stay co-resident
+        else if (n <= 2048) r = run_persistent<2, 8, 256>(G, ldg, V, ldv, n, tol, max_sweeps);     // 256 threads x 8 rows: 2 CTAs per SM stay co-resident
+        else r = run_persistent<2, 16, 256>(G, ldg, V, ldv, n, tol, max_sweeps);                   // up to 4096: CTAs stride over the 1024+ tournament slots
         if (r >= -1) return r;
     }
     if (n > JT * JR) { set_error("rsvd_b200: Jacobi of n = %d needs the persistent kernel (cooperative launch and a rotation log of %.1f GB)", n, 40.0 * n * n / 2 * 16 / 1e9); return -1; }

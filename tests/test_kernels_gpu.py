@@ -151,7 +151,7 @@ def test_orthonormalize_exactly_rank_deficient_panel(lib, m, l, rank):
     assert np.abs(np.tril(Rn, -1)).max() == 0.0
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 33, 120, 520, 1500])
+@pytest.mark.parametrize("n", [1, 2, 5, 33, 120, 520, 1500, 2500])
 def test_jacobi_svd_and_eig(lib, n):
     rng = np.random.default_rng(n)
     U0, _ = np.linalg.qr(rng.standard_normal((n, n)))
