@@ -71,6 +71,20 @@ def test_svd_vs_golden(api, golden, name, mat):
     assert np.count_nonzero(S - np.diag(d)) == 0                               # S is a full diagonal mat
 
 
+def test_svd_with_a_sketch_wider_than_2048(api):
+    """k + p = 2120: every stage beyond the round-1 limits (one-sided Jacobi above 2048 columns, the dataflow Cholesky kernel with
+    67 x 67 blocks, GEMM tiles for 2120 columns) against the numpy twin with the same Omega."""
+    m, n, k, p = 3200, 2600, 2100, 20
+    rng = np.random.default_rng(12)
+    A = (rng.standard_normal((m, 2300)) * np.logspace(0, -5, 2300)) @ rng.standard_normal((2300, n)) / 50.0
+    U, S, V = api.svd_rand(A, k, p, 1, 2, 1, seed=777)
+    Ur, Sr, Vr = O.low_rank_svd_rand_decomp_fixed_rank(A, k, p, 1, 2, 1, seed=777)
+    assert rel_sigma_err(S, Sr) < 1e-10
+    e, er = recon_err(A, U, S, V), recon_err(A, Ur, Sr, Vr)
+    assert abs(e - er) <= 0.01 * er
+    assert np.abs(U.T @ U - np.eye(k)).max() < 1e-10 and np.abs(V.T @ V - np.eye(k)).max() < 1e-10
+
+
 @pytest.mark.parametrize("m,n,k,p,vnum,q,s,spec", [
     (2000, 1500, 100, 20, 1, 2, 1, "logspace"),    # BASELINE config 0 (reference's own spectrum)
     (2000, 1500, 100, 20, 1, 2, 1, "exp"),         # BASELINE config 0 ("exp-decaying spectrum")
