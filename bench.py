@@ -476,7 +476,7 @@ def main():
     peak_nominal = 148 * 64 * 2 * 1.965e9 / 1e12      # 64 FP64 FMA/clk/SM at clocks.max.sm
     peak = max(peak_dmma, 0.0)
     traffic = None
-    tf_file = os.path.join(ROOT, "profiles", "r1_gemm_tma_dram_bytes.json")
+    tf_file = os.path.join(ROOT, "profiles", "r2_gemm_tma_dram_bytes.json")     # from the round-2 `ncu --set full` capture of the same kernels
     if os.path.exists(tf_file):
         try:
             traffic = json.load(open(tf_file)).get("dram_bytes_per_launch")
