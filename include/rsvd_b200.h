@@ -40,10 +40,11 @@ unsigned long long rsvd_b200_launch_count(void); /* kernels launched by this lib
  * ignore the worker pool); A/B switches of individual kernels, all default 0: "no_sketch_cluster", "no_chol_dataflow" (l x l
  * Cholesky + inverse as a per-block launch sequence), "no_live_replay" (Jacobi's V rebuilt after the rotations instead of next
  * to them), "no_block_cache" (freed work buffers go straight back to the CUDA memory pool), "jacobi_transpose";
+ * "qr_blocked_rows" (inputs with at most this many rows use the blocked pivoted QR; default 2048, at most 4096);
  * in a process-per-GPU job "row0" / "m_global" place this rank's row block in the global matrix.
  * "last_qr_path": 1 CholeskyQR2, 4 shifted CholeskyQR3, 2 TSQR-preconditioned, 3 Householder with explicit Q (singular panel). */
 void rsvd_b200_set_option(const char *name, rsvd_i64 value);
-rsvd_i64 rsvd_b200_get_option(const char *name); /* also "last_gemm_path", "last_qr_path", "qr_fallbacks", "sms" */
+rsvd_i64 rsvd_b200_get_option(const char *name); /* also "last_gemm_path", "last_qr_path", "qr_fallbacks", "sms", "rank", "world", "devices" (workers of the single-process pool) */
 
 /* ---- memory --------------------------------------------------------------------------------------- */
 double *rsvd_b200_dev_alloc(rsvd_i64 n_doubles);

@@ -242,3 +242,17 @@ def test_binary_loader_multi_block_and_truncated(tmp_path):
     B = api.from_mat(M)
     assert B.shape == (m, n) and np.array_equal(B[:8], A[:8])
     api.lib.rsvd_b200_api_clear_error()
+
+
+def test_every_runtime_option_is_documented_in_the_header():
+    """rsvd_b200_set_option / get_option accept exactly the names runtime.cu compares against; each must appear in the option
+    comment of include/rsvd_b200.h (an undocumented switch is an interface nobody can rely on)."""
+    import re
+    src = open(os.path.join(ROOT, "lowrankmatrixdecompositioncodes_b200", "csrc", "device", "runtime.cu")).read()
+    body = src[src.index("void rsvd_b200_set_option("):]
+    body = body[:body.index("\n}\n", body.index("rsvd_i64 rsvd_b200_get_option("))]
+    names = set(re.findall(r'!strcmp\(name, "([a-z0-9_]+)"\)', body))
+    assert {"seed", "verbose", "no_chol_dataflow", "no_live_replay", "no_block_cache", "last_qr_path"} <= names
+    header = open(os.path.join(ROOT, "include", "rsvd_b200.h")).read()
+    missing = sorted(n for n in names if '"%s"' % n not in header)
+    assert not missing, "options missing from include/rsvd_b200.h: %s" % missing
