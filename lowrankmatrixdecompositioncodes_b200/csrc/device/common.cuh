@@ -48,6 +48,19 @@ struct Ctx {
     long long m_global = 0;          // total rows of the row-partitioned matrix (0 = not partitioned)
     long long row0 = 0;              // global index of this rank's first row (left sketches index Omega by global row)
     void *nccl_comm = nullptr;
+    // peer mailboxes of the row/column-sharded pivoted QR (dist.cu: peer_mailbox): a block of this rank's HBM that every other
+    // rank of the communicator has mapped (CUDA IPC between processes, peer access inside one process)
+    struct PeerBox {
+        int state = 0;                           // 0 not set up yet, 1 usable, -1 unavailable (the QR falls back to ncclAllGather)
+        void *block = nullptr;                   // flags (2 x world u64, padded) followed by 2 x world records
+        unsigned long long *flag = nullptr;      // this rank's flags   [parity][sender]
+        double *cand = nullptr;                  // this rank's records [parity][sender][rec_max]
+        unsigned long long **d_peer_flag = nullptr;   // device arrays [world]: the same two pointers on every rank
+        double **d_peer_cand = nullptr;
+        size_t rec_max = 0;
+        unsigned long long token = 0;            // steps exchanged so far (identical on all ranks): step tokens and buffer parity
+        int *err = nullptr;                      // device flag: a wait timed out
+    } peer;
     // statistics
     unsigned long long launches = 0;
     int verbose = 0;
@@ -189,6 +202,7 @@ void jacobi_eig(double *A, i64 lda, i64 n, double *w);
 // ---- collectives (dist.cu) ---------------------------------------------------------------------
 void allreduce_sum(double *d, size_t count);      // no-op when world == 1
 void allgather(const double *send, double *recv, size_t count);   // recv = [rank 0's count doubles | rank 1's | ...]
+bool peer_mailbox(size_t rec_doubles);     // collective (every rank of the communicator calls it at the same point); true = ctx().peer usable
 int nccl_unique_id(char id_out[128]);
 int nccl_join(int rank, int world, const char id[128]);            // the calling thread's context joins a communicator
 void nccl_leave();

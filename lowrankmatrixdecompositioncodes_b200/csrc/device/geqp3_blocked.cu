@@ -89,6 +89,7 @@ struct StepP {
     double *tau, *aux;        // tau[kmax]; aux[QNB] = -tau V^T v
     double *part_v; int *part_pos, *part_c; int nparts;
     double *cand_send, *cand_all;     // (CAND_HDR + m) doubles per rank
+    i64 cand_stride;                  // doubles between two ranks' records in cand_all (0: CAND_HDR + m, the all-gather layout)
     int ps_formula, downdate;
 };
 
@@ -143,7 +144,7 @@ __device__ void reflect_phase(const StepP &p, const double *cand_all, const doub
     __shared__ int s_w;
     __shared__ double s_tau, s_scal, s_beta;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int rec = CAND_HDR + p.m;
+    const i64 rec = p.cand_stride ? p.cand_stride : (i64)(CAND_HDR + p.m);
     if (tid == 0) {
         int w = 0; double bv = cand_all[0]; int bp = (int)cand_all[1];
         for (int g = 1; g < p.world; ++g) {
@@ -211,6 +212,54 @@ __device__ void reflect_phase(const StepP &p, const double *cand_all, const doub
 
 __global__ void __launch_bounds__(1024) qp_candidate_kernel(StepP p) { candidate_phase(p, nullptr); }
 __global__ void __launch_bounds__(1024) qp_reflect_kernel(StepP p) { reflect_phase(p, p.cand_all, nullptr); }
+// Several ranks, exchange through the peer mailboxes (dist.cu: peer_mailbox): the candidate record goes straight into every
+// peer's HBM over NVLink, a system-scope release store publishes the step's token, and the CTA waits for the tokens of all
+// peers before the (replicated) reflector phase — one launch per step instead of candidate kernel + ncclAllGather + reflect
+// kernel.  Two record buffers alternate with the parity of the token; a rank can be at most one step ahead of a peer (it
+// needs the peer's record of the current step to finish it), so the buffer being read is never the one being written.
+struct PeerArgs {
+    double *const *peer_cand; unsigned long long *const *peer_flag;   // [world], the same layout on every rank
+    double *cand; unsigned long long *flag;                            // this rank's mailbox
+    unsigned long long token; i64 rec_max; int rank; int *err;
+};
+__global__ void __launch_bounds__(1024) qp_pivot_peer_kernel(StepP p, PeerArgs a) {
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, nt = blockDim.x, world = p.world;
+    const int parity = (int)(a.token & 1ull);
+    const i64 slot = ((i64)parity * world + a.rank) * a.rec_max;
+    if (tid == 0) s_bad = *((volatile int *)a.err);
+    p.cand_send = a.cand + slot;                               // phase 1 writes the record into this rank's own slot
+    candidate_phase(p, nullptr);
+    __syncthreads();
+    if (s_bad) return;                                         // an earlier step timed out: do not wait again (the host reports it)
+    const int rec = CAND_HDR + p.m;
+    const double *mine = a.cand + slot;
+    for (int g = 0; g < world; ++g) {
+        if (g == a.rank) continue;
+        double *dst = a.peer_cand[g] + slot;
+        for (int r = tid; r < rec; r += nt) dst[r] = mine[r];
+    }
+    __threadfence_system();                                    // every thread's remote stores before the token
+    __syncthreads();
+    if (tid < world) {
+        unsigned long long *f = a.peer_flag[tid] + (parity * world + a.rank);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.token) : "memory");
+    }
+    if (tid < world) {
+        const unsigned long long *f = a.flag + (parity * world + tid);
+        unsigned long long v;
+        long long spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= a.token) break;
+            if (++spins > (1ll << 22)) { s_bad = 1; *a.err = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (s_bad) return;
+    p.cand_stride = a.rec_max;
+    reflect_phase(p, a.cand + (i64)parity * world * a.rec_max, nullptr);
+}
 __global__ void __launch_bounds__(1024) qp_pivot_fused_kernel(StepP p) {   // one rank: no exchange between the phases
     extern __shared__ double ush[];                    // m doubles: the candidate column
     candidate_phase(p, ush);
@@ -460,6 +509,15 @@ void qp_factor(double *A, i64 lda, int m, int nloc, int col0, int n_global, bool
     p.Rpiv = W.Rpiv.p; p.ldr = kmax; p.tau = W.tau.p; p.aux = W.aux.p;
     p.part_v = W.part_v.p; p.part_pos = W.part_pos; p.part_c = W.part_c; p.nparts = wide_blocks;
     p.cand_send = W.cand_send.p; p.cand_all = W.cand_all.p;
+    p.cand_stride = 0;
+    // several ranks: exchange the candidate records through the peer mailboxes when every rank could map them (collective
+    // set-up on first use), else through ncclAllGather
+    const bool use_peer = world > 1 && peer_mailbox((size_t)(CAND_HDR + m));
+    PeerArgs pa;
+    if (use_peer) {
+        pa.peer_cand = c.peer.d_peer_cand; pa.peer_flag = c.peer.d_peer_flag; pa.cand = c.peer.cand; pa.flag = c.peer.flag;
+        pa.rec_max = (i64)c.peer.rec_max; pa.rank = c.rank; pa.err = c.peer.err; pa.token = 0;
+    }
     const bool blocked_range = kmax > 128;            // dgeqp3: NB = 32 < sminmn and NX = 128 < sminmn
     int k0 = 0;
     for (int k = 0; k < kmax && !g_status; ++k) {
@@ -468,6 +526,10 @@ void qp_factor(double *A, i64 lda, int m, int nloc, int col0, int n_global, bool
         p.downdate = (k < kmax - 1) ? 1 : 0;                        // dlaqps/dlaqp2: no downdate at the last row
         if (world == 1) {
             qp_pivot_fused_kernel<<<1, 1024, (size_t)m * sizeof(double), c.stream>>>(p);
+            count_launch();
+        } else if (use_peer) {
+            pa.token = c.peer.token + (unsigned long long)k + 1ull;
+            qp_pivot_peer_kernel<<<1, 1024, 0, c.stream>>>(p, pa);
             count_launch();
         } else {
             qp_candidate_kernel<<<1, 1024, 0, c.stream>>>(p);
@@ -491,6 +553,13 @@ void qp_factor(double *A, i64 lda, int m, int nloc, int col0, int n_global, bool
         }
     }
     RSVD_CUDA(cudaGetLastError());
+    if (use_peer) {
+        c.peer.token += (unsigned long long)kmax;     // the same on every rank: tokens and buffer parity continue across factorisations
+        int bad = 0;
+        RSVD_CUDA(cudaMemcpyAsync(&bad, c.peer.err, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        RSVD_CUDA(cudaStreamSynchronize(c.stream));
+        if (bad) set_error("rsvd_b200: pivoted QR: a peer's candidate record did not arrive (peer mailbox wait timed out on rank %d)", c.rank);
+    }
 }
 
 }  // namespace
