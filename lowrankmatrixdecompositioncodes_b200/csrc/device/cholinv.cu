@@ -12,6 +12,8 @@
 // (cooperative) grid of P CTAs executes tasks p, p+P, ... in order and waits on per-block ready flags (release/acquire through
 // L2) — no device-wide barriers, no host round trips; everything that does not sit on the critical path
 // (potf2 -> panel block -> next diagonal update) runs in its shadow, including the whole inverse.
+// The diagonal task of column c additionally repeats the accumulation of C(c-1, c), so that the chain potf2 -> R(c-1,c) -> next
+// diagonal block costs one hop through L2 per block column, not two.
 // Deadlock-free: the smallest unfinished task is always being executed (its CTA has finished its earlier tasks) and all of
 // its inputs are finished tasks.  Waits are bounded spins that raise an error flag instead of hanging the GPU.
 #include "common.cuh"
@@ -198,6 +200,39 @@ __global__ void __launch_bounds__(CT) chol_inv_kernel(double *G, i64 ldg, int n,
                     const int gi = r * CB + ty + 16 * i, gj = c * CB + tx + 8 * j;
                     acc[i][j] = (gi < n && gj < n) ? G[(i64)gj * ldg + gi] : (gi == gj ? 1.0 : 0.0);
                 }
+            if (r == c && c > 0) {
+                // Diagonal block: its last input, R(c-1, c), is one L2 hop behind W_{c-1} (task C(c-1, c) has to see the flag, load
+                // W, multiply, store, publish).  The diagonal task keeps its own copy of that task's accumulation instead
+                // (accP = G(c-1,c) - sum_{j<c-1} R(j,c-1)^T R(j,c): off the critical path, the inputs are old) and forms
+                // R(c-1, c) = W_{c-1}^T accP itself as soon as W_{c-1} is published: one hop per block column instead of two.
+                double accP[2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int gi = (c - 1) * CB + ty + 16 * i, gj = c * CB + tx + 8 * j;
+                        accP[i][j] = (gi < n && gj < n) ? G[(i64)gj * ldg + gi] : 0.0;
+                    }
+                for (int j = 0; j < c - 1; ++j) {
+                    if (!wait2(flagC + j * nb + c, flagC + j * nb + (c - 1), &st->err, &sh_ok)) return;
+                    load_block(As, G, ldg, j, c, n, false);          // R(j, c)
+                    load_block(Bs, G, ldg, j, c - 1, n, false);      // R(j, c-1)
+                    __syncthreads();
+                    mma32<-1>(acc, As, As);
+                    mma32<-1>(accP, Bs, As);
+                    __syncthreads();
+                }
+                if (!wait2(flagC + (c - 1) * nb + (c - 1), nullptr, &st->err, &sh_ok)) return;
+                load_block(As, X, ldx, c - 1, c - 1, n, false);      // W_{c-1}
+                acc_to_smem(accP, Bs, false);
+                __syncthreads();
+                double rl[2][4] = {};
+                mma32<1>(rl, As, Bs);                                 // R(c-1, c), the same arithmetic as task C(c-1, c)
+                acc_to_smem(rl, Ds, false);
+                __syncthreads();
+                mma32<-1>(acc, Ds, Ds);
+                __syncthreads();
+            } else
             for (int j = 0; j < r; ++j) {
                 if (!wait2(flagC + j * nb + r, flagC + j * nb + c, &st->err, &sh_ok)) return;
                 load_block(As, G, ldg, j, r, n, false);
