@@ -43,7 +43,7 @@ __device__ __forceinline__ double rsqrt1(double x) {      // 1/sqrt(x) to ~1 ulp
     double y0;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
     const double e = fma(-x * y0, y0, 1.0);
-    return fma(y0, e * fma(0.375, e, 0.5), y0);
+    return fma(y0 * e, fma(0.375, e, 0.5), y0);            // y0 e and (0.5 + 0.375 e) in parallel: four dependent operations after the seed
 }
 
 // Threads 0 and 32 (two warps) poll one flag each; everybody leaves through the barrier.  false = give up.
@@ -127,51 +127,64 @@ __device__ __forceinline__ void acc_to_smem(const double (&acc)[2][4], double *S
 }
 
 // One warp: Cholesky factor and inverse of the 32 x 32 block whose UPPER triangle is in D (column-major, stride CS).
-// Lane r carries row r of the lower factor L = R^T and row r of E, the running solution of L E = I, in registers: at column
-// c row c of E is final (scaled by 1/pivot) and every later row takes the same rank-1 update as L.  Per column: one shuffle
-// broadcasts the pivot, every lane publishes its scaled entry of column c (lane c also its final row of E) in shared memory,
-// one __syncwarp, and the rank-1 updates read them back as broadcast LDS.128 (double-buffered, so one sync per column).
+// Factor: lane r carries row r of the lower factor L = R^T in registers.  Per column: one shuffle broadcasts the pivot, every
+// lane publishes its scaled entry of column c in shared memory, one __syncwarp, and the rank-1 update reads the column back as
+// broadcast LDS (double-buffered, so one sync per column).  The chain per column is pivot -> reciprocal square root -> scale ->
+// update of the next pivot; nothing else sits on it.  Inverse: afterwards lane j solves L x = e_j by forward substitution
+// (column j of L^{-1}; rows of L are broadcast reads from shared memory) — 32 light steps instead of carrying a second
+// register matrix through the factorisation (fewer registers: 208 -> 128, so larger matrices keep 3-4 CTAs per SM: 2.59 -> 1.75 ms at n = 2048).
 // A column step is a template so that every register index is a compile-time constant; failure handling is branch-free
-// (a divergent branch makes ptxas wrap every later shuffle in WARPSYNC/ENDCOLLECTIVE pairs: about 25k instructions in this kernel instead of 9k).
+// (a divergent branch makes ptxas wrap every later shuffle in WARPSYNC/ENDCOLLECTIVE pairs).
 // Out: Rs = R (upper, zeros below), Ws = R^{-1} (upper, zeros below); both column-major with stride CS.
 template <int c>
-__device__ __forceinline__ void potf2_col(double (&L)[CB], double (&E)[CB], int lane, double *buf, int &bad) {
-    double d = __shfl_sync(0xffffffffu, L[c], c);
+__device__ __forceinline__ void potf2_col(double (&L)[CB], double pv, int lane, double *buf, double *dinv, int &bad) {
+    // pv: lane c holds the pivot (its L[c] after the updates of columns < c), computed WITHOUT the shared-memory round trip
+    double d = __shfl_sync(0xffffffffu, pv, c);
     const bool neg = !(d > 0.0);                             // warp-uniform; keep going with finite numbers, the caller discards the result
     bad = (neg && bad == 0) ? c + 1 : bad;
     d = neg ? 1.0 : d;
     const double inv = rsqrt1(d);
-    double *colb = buf + (c & 1) * (2 * CB), *erow = colb + CB;
+    double *colb = buf + (c & 1) * CB;
     const double lrc = (lane > c) ? L[c] * inv : 0.0;
     L[c] = (lane == c) ? d * inv : lrc;
     colb[lane] = lrc;
-    if (lane == c) {
-#pragma unroll
-        for (int k = 0; k <= c; ++k) { E[k] *= inv; erow[k] = E[k]; }
-    }
+    if (lane == 0) dinv[c] = inv;
+    // the next pivot lives on lane c + 1 and only needs that lane's own lrc: keep it off the STS -> LDS path
+    double pv_next = 0.0;
+    if constexpr (c + 1 < CB) pv_next = fma(-lrc, lrc, L[c + 1]);
     __syncwarp();
 #pragma unroll
     for (int k = c + 1; k < CB; ++k) L[k] = fma(-lrc, colb[k], L[k]);     // entries k > lane are never read
+    if constexpr (c + 1 < CB) potf2_col<c + 1>(L, pv_next, lane, buf, dinv, bad);
+}
+template <int k>
+__device__ __forceinline__ void trtri_col(double (&x)[CB], int lane, const double *Ls, const double *dinv) {
+    // right-looking forward substitution for column `lane` of E = L^{-1}: x[k] holds delta_{k,lane} - sum_{j<k} L(k,j) E(j,lane) on
+    // entry; finish it, then push its contribution into every later row (independent updates: the chain is one FMA per step)
+    const double xk = (lane > k) ? 0.0 : x[k] * dinv[k];
+    x[k] = xk;
 #pragma unroll
-    for (int k = 0; k <= c; ++k) E[k] = fma(-lrc, erow[k], E[k]);         // lanes <= c: lrc = 0, rows stay
-    if constexpr (c + 1 < CB) potf2_col<c + 1>(L, E, lane, buf, bad);
+    for (int i = k + 1; i < CB; ++i) x[i] = fma(-Ls[k + CS * i], xk, x[i]);          // Ls[k + CS*i] = L(i, k) = R(k, i)
+    if constexpr (k + 1 < CB) trtri_col<k + 1>(x, lane, Ls, dinv);
 }
 __device__ __forceinline__ void potf2_inv_warp(const double *D, double *Rs, double *Ws, double *buf, int gcol0, int *fail) {
     const int lane = threadIdx.x & 31;
-    double L[CB], E[CB];
+    double L[CB];
 #pragma unroll
-    for (int c = 0; c < CB; ++c) {
-        L[c] = (c <= lane) ? D[c + CS * lane] : 0.0;
-        E[c] = (c == lane) ? 1.0 : 0.0;
-    }
+    for (int c = 0; c < CB; ++c) L[c] = (c <= lane) ? D[c + CS * lane] : 0.0;
     int bad = 0;
-    potf2_col<0>(L, E, lane, buf, bad);
+    double *dinv = buf + 2 * CB;
+    potf2_col<0>(L, L[0], lane, buf, dinv, bad);
     if (bad && lane == 0) atomicCAS(fail, 0, gcol0 + bad);
 #pragma unroll
-    for (int c = 0; c < CB; ++c) {
-        Rs[c + CS * lane] = (c <= lane) ? L[c] : 0.0;       // R(c, lane) = L(lane, c)
-        Ws[c + CS * lane] = (c <= lane) ? E[c] : 0.0;       // R^{-1}(c, lane) = E(lane, c)
-    }
+    for (int c = 0; c < CB; ++c) Rs[c + CS * lane] = (c <= lane) ? L[c] : 0.0;       // R(c, lane) = L(lane, c)
+    __syncwarp();
+    double x[CB];
+#pragma unroll
+    for (int i = 0; i < CB; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
+    trtri_col<0>(x, lane, Rs, dinv);
+#pragma unroll
+    for (int i = 0; i < CB; ++i) Ws[lane + CS * i] = x[i];                           // R^{-1}(lane, i) = E(i, lane); zero for i < lane
 }
 
 __global__ void __launch_bounds__(CT) chol_inv_kernel(double *G, i64 ldg, int n, double *X, i64 ldx, int nb, int *flagC, int *flagX,
