@@ -347,8 +347,12 @@ static void id_tail(double *Y, i64 ldy, i64 r, i64 n, i64 k, double *I, double *
 static void id_tail_transposed(const double *Xt, i64 ldx, i64 nloc_in, i64 rows0, i64 n_global, i64 r, i64 k, double *I, double *T, i64 ldt) {
     Ctx &c = ctx();
     const int W = c.world;
-    if (!geqp3_blocked_ok(r, n_global) || c.force_unblocked_qr || W == 1) {
-        if (W > 1 && rows0 >= 0) { set_error("rsvd_b200: the sharded pivoted QR needs <= 4096 rows (got %lld)", (long long)r); return; }
+    // A born-sharded input can only go through the blocked (shardable) kernel: it takes up to 4096 rows there whatever the
+    // "qr_blocked_rows" preference for single-GPU inputs says.
+    const bool sharded_in = W > 1 && rows0 >= 0;
+    const bool blocked_ok = sharded_in ? (r >= 1 && r <= 4096 && n_global < (1ll << 31) - 64) : geqp3_blocked_ok(r, n_global);
+    if (!blocked_ok || (c.force_unblocked_qr && !sharded_in) || W == 1) {
+        if (sharded_in) { set_error("rsvd_b200: the sharded pivoted QR needs <= 4096 rows (got %lld)", (long long)r); return; }
         DBuf Y((size_t)r * n_global);
         transpose(Xt, ldx, Y.p, r, n_global, r);
         id_tail(Y.p, r, r, n_global, k, I, T, ldt);

@@ -53,7 +53,10 @@ def gather_rows(t_cm, m_loc, cols):
 
 
 L = ref_lib.RefLib(32) if ref_lib.available(32) else None
-for (m, n, k, p, q, s, spec) in [(2000, 1500, 100, 20, 2, 1, "gap"), (3001, 900, 40, 10, 2, 1, "logspace")]:
+CASES = [(2000, 1500, 100, 20, 2, 1, "gap"), (3001, 900, 40, 10, 2, 1, "logspace")]
+if os.environ.get("DIST_CHECK_WIDE"):      # k + p beyond 2048: Jacobi above 2048 columns, sharded pivoted QR with 2100 rows
+    CASES = [(6000, 5000, 2100, 20, 2, 1, "logspace")]
+for (m, n, k, p, q, s, spec) in CASES:
     A, sig = O.make_matrix(m, n, spec, seed=3, k=k, tail=1e-7)
     r0, rows = native.row_partition(m, world, rank)
     lib.rsvd_b200_set_option(b"row0", r0)
